@@ -1,0 +1,221 @@
+/*
+ * pyqmd_b200.h -- C ABI of libpyqmd_b200.so: PyQMD's hot path (all-pairs nucleon force ->
+ * damped Euler integrate -> per-nucleus stochastic decay) on NVIDIA B200 (sm_100a).
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All device pointers are caller
+ * owned (e.g. torch tensors).  Every call is stream-ordered and non-blocking unless it is a
+ * *_host entry point.  Return value: 0 on success, negative PYQMD_ERR_* otherwise (no
+ * exceptions cross the ABI); pyqmd_last_error() gives the message for the calling thread.
+ *
+ * Each entry point names the reference interface it replaces (file:line relative to the
+ * root of OtsoBear/PyQMD).  The reference binds its device code through PyOpenCL
+ * (nuclear_forces.py:174-183, 212-220); INTEGRATION.md shows the ctypes stub that replaces
+ * that binding.
+ */
+#ifndef PYQMD_B200_H
+#define PYQMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYQMD_ABI_VERSION 1
+
+#define PYQMD_OK 0
+#define PYQMD_ERR_INVALID (-1)   /* bad argument */
+#define PYQMD_ERR_CUDA (-2)      /* CUDA runtime error (see pyqmd_last_error) */
+#define PYQMD_ERR_NO_DEVICE (-3) /* no usable sm_100 device */
+#define PYQMD_ERR_CAPACITY (-4)  /* a caller-supplied buffer is too small */
+
+/* ParticleType, particles.py:5-11 */
+enum {
+    PYQMD_PT_PROTON = 0, PYQMD_PT_NEUTRON = 1, PYQMD_PT_ALPHA = 2, PYQMD_PT_ELECTRON = 3,
+    PYQMD_PT_GAMMA = 4, PYQMD_PT_POSITRON = 5
+};
+/* DecayType, particles.py:13-21 */
+enum {
+    PYQMD_DECAY_NONE = 0, PYQMD_DECAY_ALPHA = 1, PYQMD_DECAY_BETA_MINUS = 2,
+    PYQMD_DECAY_BETA_PLUS = 3, PYQMD_DECAY_GAMMA = 4, PYQMD_DECAY_NEUTRON = 5,
+    PYQMD_DECAY_PROTON = 6, PYQMD_DECAY_FISSION = 7
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* library                                                                                   */
+int pyqmd_abi_version(void);
+const char *pyqmd_last_error(void);
+/* out[0]=SM count, [1]=cc major, [2]=cc minor, [3]=max SM clock kHz, [4]=L2 bytes,
+ * [5]=max dynamic smem per block, [6]=total global memory MiB, [7]=reserved */
+int pyqmd_device_props(int device, int64_t out[8]);
+/* FP32 FMA peak microbenchmark on the current device (dependent FFMA chains, 8 per thread):
+ * writes achieved TFLOP/s for scalar FFMA and for packed fma.rn.f32x2. */
+int pyqmd_fp32_peak(int iters, double *tflops_ffma, double *tflops_ffma2, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* (A) reference-shaped, host buffers, blocking                                              */
+
+/*
+ * Replaces the OpenCL kernel launch inside NuclearForces.update_particles_gpu
+ * (nuclear_forces.py:202-227: H2D x2, kernel `update_forces_and_positions` :60-68, wait, D2H)
+ * with the same argument list: `particles` = float32[n][4] (x, y, vx, vy) as h_particles
+ * (:190-198), `types` = int32[n], 0 proton / 1 neutron (:199), centre (:206-208), strengths
+ * (:216-218), dt (:219).  Updated in place.  Unlike the reference kernel (in-place, racy,
+ * :168-171) the step is Jacobi, i.e. the semantics of update_particles_cpu (:236-323).
+ */
+int pyqmd_update_forces_and_positions(float *particles, const int32_t *types, int32_t num_particles,
+                                      float center_x, float center_y, float strong_strength,
+                                      float coulomb_strength, float pauli_strength, float dt);
+
+/*
+ * Replaces NuclearForces.update_particles_cpu / _gpu as a whole (nuclear_forces.py:185-323)
+ * for callers that keep float64 state (Particle.x/.y/.vx/.vy are Python floats,
+ * particles.py:24-29): centre of mass (:242-243) is taken in float64, positions are made
+ * nucleus-relative before the FP32 device step and restored afterwards, `n_steps` sub-steps
+ * run back to back on the device (nuclear_sim.py:161-173 without decay).
+ */
+int pyqmd_update_particles_f64(double *x, double *y, double *vx, double *vy,
+                               const uint8_t *is_proton, int64_t n, double strong_strength,
+                               double coulomb_strength, double pauli_strength, double dt,
+                               int32_t n_steps);
+
+/* ---------------------------------------------------------------------------------------- */
+/* (B) one large nucleon cloud resident on the device (BASELINE config 4)                    */
+
+/* bytes of scratch pyqmd_cloud_step needs for n nucleons */
+int64_t pyqmd_cloud_workspace_bytes(int64_t n);
+
+/*
+ * One Jacobi step of nuclear_forces.py:236-323 for nucleons [i0, i1) of an n-nucleon cloud.
+ *   pos_in   float2[n]  positions at step start (a full replica on every GPU)
+ *   pos_out  float2[n]  new positions, written for [i0, i1) only (all-gather afterwards)
+ *   vel      float2[n]  velocities, updated in place for [i0, i1)
+ *   force    float2[n]  optional (may be NULL): pre-integration force for [i0, i1)
+ *   is_proton uint8[n]  1 proton / 0 neutron
+ * Correct for any particle order; fastest when the caller keeps the cloud partitioned by
+ * type and spatially sorted (pyqmd_cloud_sort_keys), which lets whole 256-nucleon tiles take
+ * the far-field fast path.  The centre of mass (:242-243) is reduced on the device in a
+ * fixed order, identically on every rank.
+ */
+int pyqmd_cloud_step(const float *pos_in, float *pos_out, float *vel, float *force,
+                     const uint8_t *is_proton, int64_t n, int64_t i0, int64_t i1, float strong,
+                     float coulomb, float pauli, float dt, void *workspace, void *stream);
+
+/* 64-bit sort keys: bit 63 = neutron, low bits = 2-D Morton code of the position inside
+ * [xmin, xmin+extent) x [ymin, ymin+extent).  Sorting by key gives the layout above. */
+int pyqmd_cloud_sort_keys(const float *pos, const uint8_t *is_proton, int64_t n, float xmin,
+                          float ymin, float extent, uint64_t *keys, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* (C)+(D) decay tables                                                                      */
+
+#define PYQMD_TABLE_ZDIM 128
+#define PYQMD_TABLE_NDIM 192
+enum { PYQMD_HL_INF = 0, PYQMD_HL_TABLE = 1, PYQMD_HL_BAND = 2 };
+
+/* One (Z, N) row of the dense nuclide table, index Z * PYQMD_TABLE_NDIM + N.
+ * Built on the host from HALF_LIVES / DECAY_CHAINS and the two heuristics
+ * (decay_chains.py:13-167, 169-201, 247-328) by pyqmd_b200/nuclides.py. */
+typedef struct {
+    double half_life;   /* PYQMD_HL_TABLE: database value, seconds (may be +inf)  :257-262 */
+    double p_decay;     /* probability per sub-step for this run's dt_decay, computed on the
+                           host exactly as particles.py:134-144; < 0 = stable (no draw) */
+    double band_a, band_b, band_unit; /* PYQMD_HL_BAND: 10**uniform(a,b)*unit     :311-328 */
+    double opt_cum[2];  /* running sums of the branch probabilities               :222-227 */
+    int32_t opt_zn[2];  /* daughter (Z << 16) | N                                             */
+    int32_t opt_mode[2];/* PYQMD_DECAY_*                                                      */
+    int32_t n_opt;      /* 1 or 2                                                             */
+    int32_t kind;       /* PYQMD_HL_*                                                         */
+} pyqmd_nuclide_entry;
+
+/* One decay event (what handle_decay appends to self.particles, nuclear_sim.py:294,349). */
+typedef struct {
+    int64_t nucleus;    /* global nucleus id */
+    int32_t step;       /* sub-step index */
+    int32_t mode;       /* PYQMD_DECAY_* */
+    int32_t zn_new;     /* daughter (Z << 16) | N */
+    int32_t ptype;      /* emitted PYQMD_PT_*, -1 if none */
+    double x, y;        /* emission point = new centre of mass (:291-294) + origin */
+    double vx, vy;      /* speed * (cos, sin)(2 pi u)  decay_chains.py:331-371 */
+} pyqmd_decay_event;
+
+/* ---------------------------------------------------------------------------------------- */
+/* (C) ensembles of independent nuclei, one (or several small) nuclei per thread block       */
+
+typedef struct {
+    /* nucleon state, CSR by nucleus, nucleus-relative FP32 (Particle, particles.py:23-39) */
+    float *pos;               /* float2[total slots] */
+    float *vel;               /* float2[total slots] */
+    uint8_t *is_proton;       /* [total slots] */
+    const int64_t *offset;    /* [n_nuclei] first slot of each nucleus */
+    int32_t *count;           /* [n_nuclei] live nucleons (shrinks on alpha / n / p emission) */
+    /* nucleus state (Nucleus, particles.py:52-60) */
+    int32_t *zn;              /* (Z << 16) | N */
+    double *half_life;        /* Nucleus.stability */
+    double *p_decay;          /* probability per sub-step; < 0 = stable */
+    const double *origin;     /* double[n_nuclei][2] added to emission points, or NULL */
+    const float *centre;      /* optional float2[n_nuclei]: containment centre supplied by the
+                                 caller (the `center` kernel argument, nuclear_forces.py:64)
+                                 instead of the mean position; NULL = compute (:242-243) */
+    int64_t n_nuclei;
+    int64_t id_base;          /* global id of nucleus 0 (RNG counters, event records) */
+    /* the nuclei this launch handles */
+    const int32_t *list;      /* [n_list] local nucleus indices, or NULL = 0..n_nuclei-1 */
+    int64_t n_list;
+    int32_t cap;              /* max nucleons of any listed nucleus (<= 1024) */
+    int32_t decay_enabled;
+    /* physics */
+    float strong, coulomb, pauli, dt_phys;   /* nuclear_forces.py:13-15; nuclear_sim.py:145 */
+    double dt_decay;                         /* nuclear_sim.py:165 */
+    /* decay inputs */
+    const pyqmd_nuclide_entry *table;
+    const double *uniforms;   /* optional [n_steps][uniforms_n][4] draws, else Philox(seed) */
+    int64_t uniforms_n;
+    uint64_t seed;
+    uint32_t step0;           /* index of the first sub-step of this call */
+    uint32_t reserved;
+    /* outputs */
+    pyqmd_decay_event *events;
+    int64_t event_capacity;
+    unsigned long long *event_count;   /* device counter; events beyond capacity are counted
+                                          but not stored */
+    unsigned long long *mode_counts;   /* [8] decays by PYQMD_DECAY_* */
+} pyqmd_ensemble;
+
+/*
+ * n_steps passes of the sub-step loop body nuclear_sim.py:165-173 for every listed nucleus:
+ * should_decay (particles.py:126-147) -> physics slice of handle_decay (nuclear_sim.py:213,
+ * 288-294, 349, 353) -> force + integrate (nuclear_forces.py:236-323).  State stays in shared
+ * memory between the n_steps sub-steps.
+ */
+int pyqmd_ensemble_step(const pyqmd_ensemble *e, int32_t n_steps, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* (D) decay-only population of particle-less nuclei (decay_chains.py:390-421; config 5)     */
+
+#define PYQMD_COUNT_COLS 16   /* per step: decays by mode [0..7], decays of watch_zn[k] [8..15] */
+
+typedef struct {
+    int32_t *zn;
+    double *half_life;
+    double *p_decay;
+    int64_t n;
+    int64_t id_base;
+    const pyqmd_nuclide_entry *table;
+    double dt_decay;
+    const double *uniforms;   /* optional [n_steps][uniforms_n][4] */
+    int64_t uniforms_n;
+    uint64_t seed;
+    uint32_t step0;
+    int32_t n_watch;
+    int32_t watch_zn[8];
+    unsigned long long *step_counts;   /* [n_steps][PYQMD_COUNT_COLS], accumulated into */
+    uint8_t *decided;         /* optional [n_steps][n]: 1 where should_decay fired */
+} pyqmd_population;
+
+int pyqmd_population_step(const pyqmd_population *p, int32_t n_steps, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYQMD_B200_H */

@@ -1,0 +1,388 @@
+// cloud.cu -- one large nucleon cloud: j-tiled all-pairs force + containment + damped Euler
+// for an i-block of the cloud (sm_100a).  BASELINE config 4 (N = 1M, i-block sharded).
+//
+// Replaces NuclearForces.update_particles_cpu / the OpenCL kernel of the reference
+// (OtsoBear/PyQMD nuclear_forces.py:236-323 / :57-173) for a single big system.
+//
+// Design (B200-first, not a translation of the untiled OpenCL loop):
+//  * positions float2 SoA; 256-nucleon j tiles staged in shared memory, read back as
+//    broadcast LDS.128 (two j per load); each thread keeps kIPT i-nucleons in registers, so
+//    one smem word feeds kIPT pair evaluations;
+//  * a tile-statistics pre-pass gives every tile a bounding box and a type flag, and the
+//    fixed-order float64 centre of mass; a warp whose i bounding box is >= 9 away from a
+//    tile's box takes the branch-free far-field path (2 MUFU + 14 FMA-pipe ops per pair),
+//    everything else the general path -- the classification is warp-uniform, so there is
+//    no divergence.  With the cloud kept type-partitioned and Morton-sorted by the caller
+//    (pyqmd_cloud_sort_keys) > 99.9 % of tile visits are far;
+//  * Jacobi update: reads pos_in, writes pos_out (the reference's OpenCL kernel updates in
+//    place and races; the CPU path, which is the parity target, is Jacobi).
+#include "common.cuh"
+#include "pair_law.cuh"
+
+namespace pyqmd {
+
+constexpr int kTile = 256;      // j-tile size == tile-statistics granularity
+constexpr int kThreads = 256;   // threads per block of the force kernel
+constexpr int kIPT = 4;         // i-nucleons per thread
+constexpr int kIBlock = kThreads * kIPT;
+
+enum : int { kTileAllProton = 1, kTileAllNeutron = 2 };
+
+struct CloudWorkspace {
+    double* centre;   // [2] float64 centre of mass
+    float4* bbox;     // [n_tiles] xmin, ymin, xmax, ymax
+    double2* sums;    // [n_tiles] partial coordinate sums
+    int* flags;       // [n_tiles] kTileAll*
+};
+
+__host__ __device__ inline int64_t n_tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
+
+static CloudWorkspace carve(void* ws, int64_t n)
+{
+    const int64_t nt = n_tiles_of(n);
+    unsigned char* p = reinterpret_cast<unsigned char*>(ws);
+    CloudWorkspace w;
+    w.centre = reinterpret_cast<double*>(p);            p += 32;
+    w.bbox = reinterpret_cast<float4*>(p);              p += sizeof(float4) * nt;
+    w.sums = reinterpret_cast<double2*>(p);             p += sizeof(double2) * nt;
+    w.flags = reinterpret_cast<int*>(p);
+    return w;
+}
+
+// ---- pass 1: per-tile bounding box, type flag, coordinate sums ---------------------------------
+__global__ void __launch_bounds__(kTile) cloud_tile_stats(const float2* __restrict__ pos,
+                                                          const uint8_t* __restrict__ isp,
+                                                          int64_t n, CloudWorkspace w)
+{
+    const int64_t j = (int64_t)blockIdx.x * kTile + threadIdx.x;
+    const bool ok = j < n;
+    float2 p = ok ? pos[j] : make_float2(0.f, 0.f);
+    float xmin = ok ? p.x : INFINITY, xmax = ok ? p.x : -INFINITY;
+    float ymin = ok ? p.y : INFINITY, ymax = ok ? p.y : -INFINITY;
+    double sx = ok ? (double)p.x : 0.0, sy = ok ? (double)p.y : 0.0;
+    int np = (ok && isp[j]) ? 1 : 0, nn = (ok && !isp[j]) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        np += __shfl_xor_sync(0xffffffffu, np, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    __shared__ float4 sb[kTile / 32];
+    __shared__ double2 ss[kTile / 32];
+    __shared__ int2 sc[kTile / 32];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sb[wid] = make_float4(xmin, ymin, xmax, ymax);
+        ss[wid] = make_double2(sx, sy);
+        sc[wid] = make_int2(np, nn);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float4 b = sb[0];
+        double2 s = ss[0];
+        int2 c = sc[0];
+        for (int k = 1; k < kTile / 32; ++k) {       // fixed order: deterministic
+            b.x = fminf(b.x, sb[k].x); b.y = fminf(b.y, sb[k].y);
+            b.z = fmaxf(b.z, sb[k].z); b.w = fmaxf(b.w, sb[k].w);
+            s.x += ss[k].x; s.y += ss[k].y;
+            c.x += sc[k].x; c.y += sc[k].y;
+        }
+        w.bbox[blockIdx.x] = b;
+        w.sums[blockIdx.x] = s;
+        w.flags[blockIdx.x] = (c.y == 0 ? kTileAllProton : 0) | (c.x == 0 ? kTileAllNeutron : 0);
+    }
+}
+
+// ---- pass 2: centre of mass (nuclear_forces.py:242-243), fixed summation order -----------------
+__global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_tiles, int64_t n)
+{
+    __shared__ double2 s[256];
+    double sx = 0.0, sy = 0.0;
+    for (int64_t k = threadIdx.x; k < n_tiles; k += 256) {
+        sx += w.sums[k].x;
+        sy += w.sums[k].y;
+    }
+    s[threadIdx.x] = make_double2(sx, sy);
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s[threadIdx.x].x += s[threadIdx.x + o].x;
+            s[threadIdx.x].y += s[threadIdx.x + o].y;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        w.centre[0] = s[0].x / (double)n;
+        w.centre[1] = s[0].y / (double)n;
+    }
+}
+
+// ---- pass 3: forces + integrate ----------------------------------------------------------------
+template <int MODE /*0 none, 1 all p-p, 2 per-pair charge*/, bool CLAMP>
+__device__ __forceinline__ void far_tile(const float2* __restrict__ sxy, const float* __restrict__ st,
+                                         int jmax, const float (&xi)[kIPT], const float (&yi)[kIPT],
+                                         const float (&qi)[kIPT], float (&fx)[kIPT],
+                                         float (&fy)[kIPT], const LawParams& L)
+{
+    const float4* s4 = reinterpret_cast<const float4*>(sxy);
+    const int pairs = jmax >> 1;
+#pragma unroll 2
+    for (int jj = 0; jj < pairs; ++jj) {
+        const float4 o = s4[jj];
+        float t0 = 0.f, t1 = 0.f;
+        if (MODE == 2) { t0 = st[2 * jj]; t1 = st[2 * jj + 1]; }
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            {
+                const float dx = o.x - xi[k], dy = o.y - yi[k];
+                float s;
+                if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
+                else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
+                else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t0, L);
+                fx[k] = fmaf(dx, s, fx[k]);
+                fy[k] = fmaf(dy, s, fy[k]);
+            }
+            {
+                const float dx = o.z - xi[k], dy = o.w - yi[k];
+                float s;
+                if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
+                else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
+                else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t1, L);
+                fx[k] = fmaf(dx, s, fx[k]);
+                fy[k] = fmaf(dy, s, fy[k]);
+            }
+        }
+    }
+    if (jmax & 1) {
+        const float2 o = sxy[jmax - 1];
+        const float t0 = st[jmax - 1];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            const float dx = o.x - xi[k], dy = o.y - yi[k];
+            float s;
+            if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
+            else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
+            else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t0, L);
+            fx[k] = fmaf(dx, s, fx[k]);
+            fy[k] = fmaf(dy, s, fy[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void near_tile(const float2* __restrict__ sxy, const float* __restrict__ st,
+                                          int jmax, const float (&xi)[kIPT], const float (&yi)[kIPT],
+                                          const float (&ti)[kIPT], float (&fx)[kIPT],
+                                          float (&fy)[kIPT], const LawParams& L)
+{
+    for (int j = 0; j < jmax; ++j) {
+        const float2 o = sxy[j];
+        const float tj = st[j];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            const float dx = o.x - xi[k], dy = o.y - yi[k];
+            const float s = pair_general(dx, dy, ti[k], tj, L);
+            fx[k] = fmaf(dx, s, fx[k]);
+            fy[k] = fmaf(dy, s, fy[k]);
+        }
+    }
+}
+
+template <bool CLAMP>
+__global__ void __launch_bounds__(kThreads, 2)
+cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_out,
+                   float2* __restrict__ vel, float2* __restrict__ force,
+                   const uint8_t* __restrict__ isp, int64_t n, int64_t i0, int64_t i1,
+                   CloudWorkspace w, LawParams L, float dt, int far_enabled)
+{
+    __shared__ __align__(16) float2 sxy[kTile];
+    __shared__ float st[kTile];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t wbase = i0 + (int64_t)blockIdx.x * kIBlock + (int64_t)wid * (32 * kIPT);
+
+    float xi[kIPT], yi[kIPT], ti[kIPT], qi[kIPT], fx[kIPT], fy[kIPT];
+    float bxmin = INFINITY, bymin = INFINITY, bxmax = -INFINITY, bymax = -INFINITY;
+    bool allp = true, alln = true;
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+        int64_t i = wbase + k * 32 + lane;
+        if (i > i1 - 1) i = i1 - 1;                    // clamp: duplicates do not move the bbox
+        if (i < i0) i = i0;
+        const float2 p = pos_in[i];
+        const bool pr = isp[i] != 0;
+        xi[k] = p.x; yi[k] = p.y;
+        ti[k] = pr ? 1.0f : 0.0f;
+        qi[k] = pr ? L.C : 0.0f;
+        fx[k] = 0.f; fy[k] = 0.f;
+        bxmin = fminf(bxmin, p.x); bxmax = fmaxf(bxmax, p.x);
+        bymin = fminf(bymin, p.y); bymax = fmaxf(bymax, p.y);
+        allp = allp && pr;
+        alln = alln && !pr;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bxmin = fminf(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+        bymin = fminf(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+        bxmax = fmaxf(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+        bymax = fmaxf(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+    }
+    allp = __all_sync(0xffffffffu, allp);
+    alln = __all_sync(0xffffffffu, alln);
+
+    const int64_t n_tiles = n_tiles_of(n);
+    // software pipeline: the next tile's element is fetched into registers while the current
+    // tile is being consumed
+    float2 nxt = make_float2(0.f, 0.f);
+    float nxt_t = 0.f;
+    {
+        const int64_t j = threadIdx.x;
+        if (j < n) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+    }
+    for (int64_t tile = 0; tile < n_tiles; ++tile) {
+        __syncthreads();                               // previous tile fully consumed
+        sxy[threadIdx.x] = nxt;
+        st[threadIdx.x] = nxt_t;
+        __syncthreads();
+        {
+            const int64_t j = (tile + 1) * kTile + threadIdx.x;
+            if (j < n) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+        }
+        const int64_t rem = n - tile * kTile;
+        const int jmax = rem < kTile ? (int)rem : kTile;
+
+        // warp-uniform classification against the tile's bounding box
+        const float4 bb = w.bbox[tile];
+        const int tf = w.flags[tile];
+        const float gx = fmaxf(0.f, fmaxf(bb.x - bxmax, bxmin - bb.z));
+        const float gy = fmaxf(0.f, fmaxf(bb.y - bymax, bymin - bb.w));
+        const bool far = far_enabled && (fmaf(gx, gx, gy * gy) > 81.01f);
+        if (far) {
+            if (alln || (tf & kTileAllNeutron))
+                far_tile<0, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
+            else if (allp && (tf & kTileAllProton))
+                far_tile<1, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
+            else
+                far_tile<2, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
+        } else {
+            near_tile(sxy, st, jmax, xi, yi, ti, fx, fy, L);
+        }
+    }
+
+    // containment + integrate, nuclear_forces.py:301-323
+    const float cx = (float)w.centre[0], cy = (float)w.centre[1];
+    const float R = 2.4f * cbrtf((float)n);            // :304
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        if (i >= i0 && i < i1) {
+            float2 v = vel[i];
+            float x = xi[k], y = yi[k];
+            // containment is part of the reported force
+            const float cdx = cx - x, cdy = cy - y;
+            const float cd = sqrtf(fmaf(cdy, cdy, cdx * cdx));
+            float Fx = fx[k], Fy = fy[k];
+            if (cd > R * 1.5f && cd > 0.01f) {
+                const float cf = 0.03f * (cd - R) / cd;
+                Fx = fmaf(cf, cdx, Fx);
+                Fy = fmaf(cf, cdy, Fy);
+            }
+            v.x = fmaf(Fx, dt, v.x) * kDamp;
+            v.y = fmaf(Fy, dt, v.y) * kDamp;
+            x = fmaf(v.x, dt, x);
+            y = fmaf(v.y, dt, y);
+            pos_out[i] = make_float2(x, y);
+            vel[i] = v;
+            if (force) force[i] = make_float2(Fx, Fy);
+        }
+    }
+}
+
+// ---- sort keys -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread_bits(uint32_t v)
+{
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
+__global__ void cloud_sort_keys_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp,
+                                       int64_t n, float xmin, float ymin, float inv_extent,
+                                       uint64_t* __restrict__ keys)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 p = pos[i];
+    const float ux = fminf(fmaxf((p.x - xmin) * inv_extent, 0.f), 0.99999994f);
+    const float uy = fminf(fmaxf((p.y - ymin) * inv_extent, 0.f), 0.99999994f);
+    const uint32_t qx = (uint32_t)(ux * 16777216.f), qy = (uint32_t)(uy * 16777216.f);
+    uint64_t key = spread_bits(qx) | (spread_bits(qy) << 1);
+    if (!isp[i]) key |= (1ull << 63);
+    keys[i] = key;
+}
+
+}  // namespace pyqmd
+
+using namespace pyqmd;
+
+extern "C" int64_t pyqmd_cloud_workspace_bytes(int64_t n)
+{
+    if (n < 0) return PYQMD_ERR_INVALID;
+    const int64_t nt = n_tiles_of(n);
+    return 32 + nt * (int64_t)(sizeof(float4) + sizeof(double2) + sizeof(int)) + 64;
+}
+
+extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel, float* force,
+                                const uint8_t* is_proton, int64_t n, int64_t i0, int64_t i1,
+                                float strong, float coulomb, float pauli, float dt, void* workspace,
+                                void* stream)
+{
+    PYQMD_REQUIRE(n >= 0 && i0 >= 0 && i0 <= i1 && i1 <= n, "0 <= i0 <= i1 <= n");
+    if (n == 0 || i0 == i1) return PYQMD_OK;            // nuclear_forces.py:238-239
+    PYQMD_REQUIRE(pos_in && pos_out && vel && is_proton && workspace, "NULL pointer");
+    PYQMD_REQUIRE(pos_in != pos_out, "pos_in and pos_out must differ (Jacobi update)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const CloudWorkspace w = carve(workspace, n);
+    const int64_t nt = n_tiles_of(n);
+    PYQMD_REQUIRE(nt <= 2147483647LL, "cloud too large");
+    const LawParams L = make_law_params(strong, coulomb, pauli);
+    cloud_tile_stats<<<(unsigned)nt, kTile, 0, st>>>(reinterpret_cast<const float2*>(pos_in),
+                                                     is_proton, n, w);
+    cloud_centre<<<1, 256, 0, st>>>(w, nt, n);
+    const int64_t blocks = (i1 - i0 + kIBlock - 1) / kIBlock;
+    const int far_enabled = strong > 0.f ? 1 : 0;
+    if (L.far_needs_clamp)
+        cloud_force_kernel<true><<<(unsigned)blocks, kThreads, 0, st>>>(
+            reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(pos_out),
+            reinterpret_cast<float2*>(vel), reinterpret_cast<float2*>(force), is_proton, n, i0, i1,
+            w, L, dt, far_enabled);
+    else
+        cloud_force_kernel<false><<<(unsigned)blocks, kThreads, 0, st>>>(
+            reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(pos_out),
+            reinterpret_cast<float2*>(vel), reinterpret_cast<float2*>(force), is_proton, n, i0, i1,
+            w, L, dt, far_enabled);
+    PYQMD_CUDA_CHECK(cudaGetLastError());
+    return PYQMD_OK;
+}
+
+extern "C" int pyqmd_cloud_sort_keys(const float* pos, const uint8_t* is_proton, int64_t n,
+                                     float xmin, float ymin, float extent, uint64_t* keys,
+                                     void* stream)
+{
+    PYQMD_REQUIRE(n >= 0 && extent > 0.f, "n >= 0 and extent > 0");
+    if (n == 0) return PYQMD_OK;
+    PYQMD_REQUIRE(pos && is_proton && keys, "NULL pointer");
+    const int64_t blocks = (n + 255) / 256;
+    cloud_sort_keys_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(pos), is_proton, n, xmin, ymin, 1.0f / extent, keys);
+    PYQMD_CUDA_CHECK(cudaGetLastError());
+    return PYQMD_OK;
+}

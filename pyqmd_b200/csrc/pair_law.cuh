@@ -1,0 +1,185 @@
+// pair_law.cuh -- the PyQMD nucleon pair-force law in FP32 for sm_100a.
+//
+// Behavioural spec: NuclearForces.update_particles_cpu, nuclear_forces.py:248-298 (reference
+// root = OtsoBear/PyQMD), restated as branch-free FP32 with MUFU approximations whose error
+// (rsqrt/ex2/rcp/sqrt.approx: <= 2 ulp each) stays inside the 1e-5 per-step budget.
+// This is new code written for the B200; it is not a translation of the reference's
+// OpenCL kernel (nuclear_forces.py:57-173), which is untiled, in-place and racy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pyqmd {
+
+// Law constants (nuclear_forces.py line numbers in brackets)
+constexpr float kEps        = 0.15f;    // [275,278,281,285]
+constexpr float kSkipD2     = 0.01f;    // [257]
+constexpr float kHardD      = 4.25f;    // [264]
+constexpr float kCoreD      = 2.8f;     // [273]
+constexpr float kAttrD      = 9.0f;     // [276]
+constexpr float kPauliD     = 8.0f;     // [289]
+constexpr float kMaxForce   = 12.0f;    // [294]
+constexpr float kLog2e      = 1.4426950408889634f;
+constexpr float kDamp       = 0.85f;    // [318-319]
+
+struct LawParams {
+    float S, C, P;          // strong / coulomb / pauli strength [13-15]
+    // derived on the host once per call
+    float coreK;            // 0.7 * S            [275]
+    float attrK;            // 1.25 * S           [278]
+    float tailK;            // 0.15 * S           [281]
+    float log2TailK;        // log2(0.15 * S)  (tail coefficient folded into the exponent)
+    int   far_needs_clamp;  // 1 if |net| could reach 12 for d >= 9 with these strengths
+};
+
+__host__ inline LawParams make_law_params(float S, float C, float P)
+{
+    LawParams p;
+    p.S = S; p.C = C; p.P = P;
+    p.coreK = 0.7f * S;
+    p.attrK = 1.25f * S;
+    p.tailK = 0.15f * S;
+    p.log2TailK = (p.tailK > 0.f) ? log2f(p.tailK) : -150.f;
+    // bound of |net| on d >= 9: tail <= tailK*exp(-1.8*9/7)/9.15, coulomb <= C/81.15
+    double bound = fabs(0.15 * (double)S) * 0.09885 / 9.15 + fabs((double)C) / 81.15;
+    p.far_needs_clamp = !(bound < 11.9) || !(S > 0.f);
+    return p;
+}
+
+__device__ __forceinline__ float mufu_rsqrt(float x)
+{
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float mufu_rcp(float x)
+{
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float mufu_ex2(float x)
+{
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float mufu_sqrt(float x)
+{
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+
+// General pair: every branch of the law, evaluated with selects (no divergence).
+//   dx,dy  = r_j - r_i                                  [253-254]
+//   ti,tj  = 1.0f for a proton, 0.0f for a neutron
+// returns s such that  F_i += (dx,dy) * s   with  s = clamp(net)/d, or 0 for a skipped pair.
+// The self pair (dx = dy = 0) is skipped by the d2 < 0.01 test [257], so callers need no i != j.
+__device__ __forceinline__ float pair_general(float dx, float dy, float ti, float tj,
+                                              const LawParams& L)
+{
+    const float d2 = fmaf(dy, dy, dx * dx);                       // [255]
+    const float rinv = mufu_rsqrt(fmaxf(d2, 1e-12f));
+    const float d = d2 * rinv;                                    // [260]
+
+    // hard core: -60 * ((4.25-d)/4.25)^1.5 for d < 4.25           [264-267]
+    const float ov = fmaxf(fmaf(d, -1.0f / kHardD, 1.0f), 0.0f);
+    float net = -60.0f * ov * mufu_sqrt(ov);
+
+    // strong force: one reciprocal serves 1/(d+eps) and 1/(d2+eps) [275,278,281,285]
+    const float a = d + kEps;
+    const float b = d2 + kEps;
+    const float rab = mufu_rcp(a * b);
+    const float inv_a = rab * b;          // 1/(d+eps)
+    const float inv_b = rab * a;          // 1/(d2+eps)
+    const bool is_core = d2 < kCoreD * kCoreD;                    // [273]
+    const bool is_attr = d2 < kAttrD * kAttrD;                    // [276]
+    const float kexp = is_attr ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f);
+    const float coef = is_attr ? L.attrK : L.tailK;
+    const float e = mufu_ex2(d * kexp);                           // exp(-d/7) or exp(-1.8 d/7)
+    const float strong = is_core ? (-L.coreK * inv_b) : (coef * e * inv_a);
+    net += strong;
+
+    // Coulomb between protons                                     [284-285]
+    net = fmaf(-(L.C * ti * tj), inv_b, net);
+
+    // Pauli for equal types and d < 8                              [288-291]
+    const float pe = mufu_ex2(d * (-2.0f * kLog2e / kPauliD));
+    const bool pauli = (ti == tj) && (d2 < kPauliD * kPauliD);
+    net = pauli ? fmaf(-L.P, pe, net) : net;
+
+    net = fminf(fmaxf(net, -kMaxForce), kMaxForce);               // [294]
+    const float s = net * rinv;                                   // [297-298]: (dx*net)/d
+    return (d2 < kSkipD2) ? 0.0f : s;                             // [257]
+}
+
+// Far pair, valid only when the caller has proved d >= 9 for the pair (tile bounding boxes):
+//   net = 0.15 S exp(-1.8 d / 7)/(d + eps) - [pp] C/(d2 + eps)     [281,285]
+// Neither the hard core, the Pauli term (d < 8) nor the d2 < 0.01 skip can apply.
+// 1/(d+eps) is expanded around 1/d (eps/d <= 1/60): (1 - z + z^2 - z^3), z = eps/d, relative
+// truncation error z^4 <= 7.7e-8; this moves one MUFU op onto the FMA pipe.
+// The tail coefficient is folded into the exponent: 0.15 S exp(-k d) = 2^(log2(0.15 S) - k' d).
+// MODE 0: no Coulomb term; 1: every pair is p-p (cq ignored, C used); 2: per-pair charge
+// product cq = C * t_i * t_j supplied by the caller.
+template <int MODE, bool CLAMP>
+__device__ __forceinline__ float pair_far_impl(float dx, float dy, float cq, const LawParams& L)
+{
+    const float d2 = fmaf(dy, dy, dx * dx);
+    const float r = mufu_rsqrt(d2);
+    const float d = d2 * r;
+    const float e = mufu_ex2(fmaf(d, -1.8f * kLog2e / 7.0f, L.log2TailK));
+    float h = fmaf(r, -kEps * kEps * kEps, kEps * kEps);
+    h = fmaf(r, h, -kEps);
+    h = fmaf(r, h, 1.0f);                   // d/(d+eps)
+    const float r2 = r * r;
+    const float c = (MODE == 1) ? L.C : cq;
+    if (!CLAMP) {
+        // s = net/d = e * h / d2  (- c / ((d2+eps) d) with Coulomb)
+        float s = e * (h * r2);
+        if (MODE != 0) {
+            // 1/(d2+eps) = r2 * (1 - eps r2 + eps^2 r2^2), eps r2 <= 1.9e-3: error < 7e-9
+            float g = fmaf(r2, kEps * kEps, -kEps);
+            g = fmaf(r2, g, 1.0f);
+            s = fmaf(-c * r, g * r2, s);
+        }
+        return s;
+    } else {
+        float net = e * (h * r);
+        if (MODE != 0) {
+            float g = fmaf(r2, kEps * kEps, -kEps);
+            g = fmaf(r2, g, 1.0f);
+            net = fmaf(-c, g * r2, net);
+        }
+        net = fminf(fmaxf(net, -kMaxForce), kMaxForce);
+        return net * r;
+    }
+}
+
+template <bool PP, bool CLAMP>
+__device__ __forceinline__ float pair_far(float dx, float dy, const LawParams& L)
+{
+    return pair_far_impl<PP ? 1 : 0, CLAMP>(dx, dy, 0.f, L);
+}
+
+template <bool CLAMP>
+__device__ __forceinline__ float pair_far_q(float dx, float dy, float cq, const LawParams& L)
+{
+    return pair_far_impl<2, CLAMP>(dx, dy, cq, L);
+}
+
+// Centre-of-mass containment + damped Euler, per nucleon.
+//   [301-309]  if |c - x| > 1.5 R and > 0.01:  F += 0.03 (|c - x| - R) (c - x)/|c - x|
+//   [312-323]  v += F dt; v *= 0.85; x += v dt
+// R = 1.2 * n^(1/3) * 2.0 is computed by the caller [304].
+__device__ __forceinline__ void contain_and_integrate(float& x, float& y, float& vx, float& vy,
+                                                      float fx, float fy, float cx, float cy,
+                                                      float R, float dt)
+{
+    const float cdx = cx - x, cdy = cy - y;
+    const float cd2 = fmaf(cdy, cdy, cdx * cdx);
+    const float cd = sqrtf(cd2);
+    if (cd > R * 1.5f && cd > 0.01f) {
+        const float cf = 0.03f * (cd - R) / cd;
+        fx = fmaf(cf, cdx, fx);
+        fy = fmaf(cf, cdy, fy);
+    }
+    vx = fmaf(fx, dt, vx) * kDamp;
+    vy = fmaf(fy, dt, vy) * kDamp;
+    x = fmaf(vx, dt, x);
+    y = fmaf(vy, dt, y);
+}
+
+}  // namespace pyqmd
