@@ -48,6 +48,9 @@ const char *pyqmd_last_error(void);
 /* out[0]=SM count, [1]=cc major, [2]=cc minor, [3]=max SM clock kHz, [4]=L2 bytes,
  * [5]=max dynamic smem per block, [6]=total global memory MiB, [7]=reserved */
 int pyqmd_device_props(int device, int64_t out[8]);
+/* sizeof of the four ABI structs below, for binding self-checks:
+ * nuclide_entry, decay_event, ensemble, population */
+int pyqmd_struct_sizes(int64_t out[4]);
 /* FP32 FMA peak microbenchmark on the current device (dependent FFMA chains, 8 per thread):
  * writes achieved TFLOP/s for scalar FFMA and for packed fma.rn.f32x2. */
 int pyqmd_fp32_peak(int iters, double *tflops_ffma, double *tflops_ffma2, void *stream);
@@ -147,6 +150,8 @@ typedef struct {
     float *pos;               /* float2[total slots] */
     float *vel;               /* float2[total slots] */
     uint8_t *is_proton;       /* [total slots] */
+    float *force;             /* optional float2[total slots]: force of the last sub-step,
+                                 containment included, before integration; NULL = not kept */
     const int64_t *offset;    /* [n_nuclei] first slot of each nucleus */
     int32_t *count;           /* [n_nuclei] live nucleons (shrinks on alpha / n / p emission) */
     /* nucleus state (Nucleus, particles.py:52-60) */

@@ -193,6 +193,16 @@ extern "C" int pyqmd_device_props(int device, int64_t out[8])
     return PYQMD_OK;
 }
 
+extern "C" int pyqmd_struct_sizes(int64_t out[4])
+{
+    PYQMD_REQUIRE(out != nullptr, "out is NULL");
+    out[0] = sizeof(pyqmd_nuclide_entry);
+    out[1] = sizeof(pyqmd_decay_event);
+    out[2] = sizeof(pyqmd_ensemble);
+    out[3] = sizeof(pyqmd_population);
+    return PYQMD_OK;
+}
+
 extern "C" int pyqmd_fp32_peak(int iters, double* tflops_ffma, double* tflops_ffma2, void* stream)
 {
     PYQMD_REQUIRE(iters > 0 && tflops_ffma && tflops_ffma2, "iters > 0, outputs non-NULL");

@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
             contain_and_integrate(x, y, vel.x, vel.y, fx, fy, cx, cy, R, e.dt_phys);   // :301-323
         }
         __syncthreads();                                    // Jacobi: all reads before any write
-        if (active) sp[tid] = make_float4(x, y, tp, 0.f);
+        if (active) {
+            sp[tid] = make_float4(x, y, tp, 0.f);
+            if (e.force && s == n_steps - 1)
+                reinterpret_cast<float2*>(e.force)[off + li] = make_float2(fx, fy);
+        }
     }
 
     if (has_nuc && li < cnt) {

@@ -165,7 +165,7 @@ __device__ __forceinline__ float pair_far_q(float dx, float dy, float cq, const 
 //   [312-323]  v += F dt; v *= 0.85; x += v dt
 // R = 1.2 * n^(1/3) * 2.0 is computed by the caller [304].
 __device__ __forceinline__ void contain_and_integrate(float& x, float& y, float& vx, float& vy,
-                                                      float fx, float fy, float cx, float cy,
+                                                      float& fx, float& fy, float cx, float cy,
                                                       float R, float dt)
 {
     const float cdx = cx - x, cdy = cy - y;

@@ -1,0 +1,438 @@
+"""GPU-resident state for PyQMD's hot path: ensembles of nuclei, one big nucleon cloud, and
+decay-only populations.  PyTorch tensors own the device memory and the streams; all compute
+goes through the C ABI of libpyqmd_b200.so (include/pyqmd_b200.h).
+
+The reference (OtsoBear/PyQMD) keeps one nucleus in Python objects and re-uploads it every
+sub-step (nuclear_forces.py:190-234).  Here the state never leaves HBM between sub-steps:
+
+  NucleusEnsemble   many independent nuclei, CSR-packed, one (or several small) per thread block;
+                    per sub-step: should_decay -> handle_decay slice -> force + integrate
+                    (nuclear_sim.py:165-173), n sub-steps fused per launch
+  NucleonCloud      one all-pairs system of N nucleons (nuclear_forces.py:236-323 at scale),
+                    i-block sharded over ranks with a per-step position all-gather
+  DecayPopulation   particle-less nuclei (decay_chains.py:390-421), Monte Carlo of should_decay
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, nuclides
+
+DEFAULT_STRENGTHS = (150.0, 30.0, 35.0)          # nuclear_forces.py:13-15
+DEFAULT_DT = 1.0 / 240.0                         # nuclear_sim.py:59
+
+# readme.md:43-51 (BASELINE config 3) and nuclear_sim.py:494-504
+README_ISOTOPES = ((1, 0), (2, 2), (6, 6), (6, 8), (26, 30), (47, 60), (79, 118), (82, 126),
+                   (92, 146))
+CODE_ISOTOPES = ((1, 2), (2, 3), (6, 8), (8, 9), (26, 33), (47, 61), (79, 119), (82, 127),
+                 (92, 146))
+
+_TEMPLATES = None
+_TABLE_CACHE = {}
+
+
+def layout_templates():
+    """Reference-generated initial layouts (Nucleus.initialize_particles, particles.py:62-124),
+    64 per isotope, FP32, origin (0, 0); see tests/golden/gen_golden.py."""
+    global _TEMPLATES
+    if _TEMPLATES is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data",
+                            "layout_templates.npz")
+        _TEMPLATES = dict(np.load(path))
+    return _TEMPLATES
+
+
+def device_table(dt_decay: float, device) -> torch.Tensor:
+    key = (float(dt_decay), str(device))
+    if key not in _TABLE_CACHE:
+        tab = nuclides.build_device_table(dt_decay)
+        _TABLE_CACHE[key] = torch.from_numpy(tab.view(np.uint8).copy()).to(device)
+    return _TABLE_CACHE[key]
+
+
+def initial_half_lives(zn: np.ndarray, dt_decay: float, rng: np.random.Generator):
+    """Per-nucleus half-life and per-sub-step decay probability at creation
+    (nuclear_sim.py:116 -> get_half_life; particles.py:134-144)."""
+    T = np.empty(len(zn), np.float64)
+    p = np.empty(len(zn), np.float64)
+    for v in np.unique(zn):
+        z, n = nuclides.zn_unpack(v)
+        sel = zn == v
+        kind, value, a, b, unit = nuclides.half_life_class(z, n)
+        if kind == _lib.HL_BAND:
+            u = rng.random(int(sel.sum()))
+            Ts = np.array([nuclides.half_life_from_draw(a, b, unit, float(x)) for x in u])
+            T[sel] = Ts
+            p[sel] = [nuclides.decay_probability(t, dt_decay) for t in Ts]
+        else:
+            T[sel] = value
+            p[sel] = nuclides.decay_probability(value, dt_decay)
+    return T, p
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block of units owned by ``rank`` (nuclei for ensembles / populations)."""
+    chunk = (n + world - 1) // world
+    lo = min(rank * chunk, n)
+    return lo, min(lo + chunk, n)
+
+
+# =================================================================================================
+class NucleusEnsemble:
+    """Independent nuclei on one GPU.  Global nucleus ids ``id_base + k`` key the RNG, so results
+    do not depend on how an ensemble is split over GPUs."""
+
+    def __init__(self, zn, offsets, counts, pos, vel, is_proton, *, device="cuda",
+                 dt_phys=DEFAULT_DT, dt_decay=DEFAULT_DT, strengths=DEFAULT_STRENGTHS, seed=0,
+                 id_base=0, half_life=None, p_decay=None, origin=None, decay=True,
+                 event_capacity=1 << 20, init_seed=0, keep_force=False):
+        _lib.require_cuda()
+        self.device = torch.device(device)
+        dev = self.device
+        as_t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray)
+                                             else a, dtype=dt).contiguous().to(dev)
+        self.zn = as_t(zn, torch.int32)
+        self.offsets = as_t(offsets, torch.int64)
+        self.count = as_t(counts, torch.int32)
+        self.pos = as_t(pos, torch.float32).reshape(-1, 2).contiguous()
+        self.vel = as_t(vel, torch.float32).reshape(-1, 2).contiguous()
+        self.is_proton = as_t(is_proton, torch.uint8)
+        self.force = torch.zeros_like(self.pos) if keep_force else None
+        self.n_nuclei = int(self.zn.numel())
+        self.dt_phys, self.dt_decay = float(dt_phys), float(dt_decay)
+        self.strengths = tuple(float(s) for s in strengths)
+        self.seed, self.id_base, self.decay = int(seed), int(id_base), bool(decay)
+        self.step_index = 0
+        if half_life is None or p_decay is None:
+            T, p = initial_half_lives(self.zn.cpu().numpy(), self.dt_decay,
+                                      np.random.default_rng(init_seed))
+            half_life = T if half_life is None else half_life
+            p_decay = p if p_decay is None else p_decay
+        self.half_life = as_t(half_life, torch.float64)
+        self.p_decay = as_t(p_decay, torch.float64)
+        self.origin = None if origin is None else as_t(origin, torch.float64).reshape(-1, 2)
+        self.table = device_table(self.dt_decay, dev)
+        self.event_capacity = int(event_capacity)
+        self.events_buf = torch.zeros(self.event_capacity * _lib.EVENT_DTYPE.itemsize,
+                                      dtype=torch.uint8, device=dev)
+        self.event_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.mode_counts = torch.zeros(8, dtype=torch.int64, device=dev)
+        # size bins: nuclei with the same initial nucleon count share a launch
+        caps = self.count.cpu().numpy()
+        self.bins = []
+        uniq = np.unique(caps)
+        for cap in uniq:
+            if cap <= 0:
+                continue
+            idx = np.nonzero(caps == cap)[0].astype(np.int32)
+            lst = None if len(uniq) == 1 else torch.from_numpy(idx).to(dev)
+            self.bins.append((int(cap), lst, len(idx)))
+
+    # ---------------------------------------------------------------------------------------------
+    @classmethod
+    def from_templates(cls, isotopes, n_nuclei, *, device="cuda", id_base=0, rotate=True, **kw):
+        """Nucleus ``g = id_base + k`` gets isotope ``isotopes[g % len]``, layout template
+        ``(g // len) % 64`` and, if ``rotate``, a rigid rotation by 2*pi*((g // (64*len)) % 1024)/1024
+        (SURVEY.md section 8d synthetic inputs).  Built on the device."""
+        _lib.require_cuda()
+        dev = torch.device(device)
+        tm = layout_templates()
+        m = len(isotopes)
+        g = torch.arange(id_base, id_base + n_nuclei, device=dev, dtype=torch.int64)
+        iso = g % m
+        a_of = torch.tensor([z + n for z, n in isotopes], device=dev, dtype=torch.int64)
+        counts = a_of[iso]
+        offsets = torch.cumsum(counts, 0) - counts
+        total = int(counts.sum().item())
+        pos = torch.empty(total, 2, device=dev, dtype=torch.float32)
+        isp = torch.empty(total, device=dev, dtype=torch.uint8)
+        zn = torch.tensor([nuclides.zn_pack(z, n) for z, n in isotopes], device=dev,
+                          dtype=torch.int32)[iso]
+        for k, (z, n) in enumerate(isotopes):
+            sel = torch.nonzero(iso == k).flatten()
+            if sel.numel() == 0:
+                continue
+            a = z + n
+            txy = torch.from_numpy(tm[f"z{z}_n{n}_xy"]).to(dev)          # [64, a, 2]
+            tis = torch.from_numpy(tm[f"z{z}_n{n}_isp"]).to(dev)         # [64, a]
+            gk = g[sel]
+            t_idx = (gk // m) % txy.shape[0]
+            chunk = 1 << 18
+            for c0 in range(0, sel.numel(), chunk):
+                s = slice(c0, c0 + chunk)
+                xy = txy[t_idx[s]]                                       # [c, a, 2]
+                if rotate:
+                    ang = ((gk[s] // (m * txy.shape[0])) % 1024).to(torch.float64) * (
+                        2 * math.pi / 1024)
+                    co, si = torch.cos(ang).float()[:, None], torch.sin(ang).float()[:, None]
+                    xy = torch.stack((xy[..., 0] * co - xy[..., 1] * si,
+                                      xy[..., 0] * si + xy[..., 1] * co), -1)
+                flat = (offsets[sel[s]][:, None] + torch.arange(a, device=dev)).reshape(-1)
+                pos[flat] = xy.reshape(-1, 2)
+                isp[flat] = tis[t_idx[s]].reshape(-1)
+        vel = torch.zeros_like(pos)
+        return cls(zn, offsets, counts.to(torch.int32), pos, vel, isp, device=device,
+                   id_base=id_base, **kw)
+
+    # ---------------------------------------------------------------------------------------------
+    def _desc(self, cap, lst, n_list, uniforms):
+        d = _lib.EnsembleDesc()
+        d.pos, d.vel, d.is_proton = self.pos.data_ptr(), self.vel.data_ptr(), self.is_proton.data_ptr()
+        d.force = _lib.ptr(self.force)
+        d.offset, d.count = self.offsets.data_ptr(), self.count.data_ptr()
+        d.zn, d.half_life, d.p_decay = (self.zn.data_ptr(), self.half_life.data_ptr(),
+                                        self.p_decay.data_ptr())
+        d.origin = _lib.ptr(self.origin)
+        d.centre = None
+        d.n_nuclei, d.id_base = self.n_nuclei, self.id_base
+        d.list, d.n_list = _lib.ptr(lst), n_list
+        d.cap, d.decay_enabled = cap, 1 if self.decay else 0
+        d.strong, d.coulomb, d.pauli = self.strengths
+        d.dt_phys, d.dt_decay = self.dt_phys, self.dt_decay
+        d.table = self.table.data_ptr()
+        d.uniforms, d.uniforms_n = _lib.ptr(uniforms), self.n_nuclei
+        d.seed, d.step0 = self.seed, self.step_index
+        d.events, d.event_capacity = self.events_buf.data_ptr(), self.event_capacity
+        d.event_count, d.mode_counts = self.event_count.data_ptr(), self.mode_counts.data_ptr()
+        return d
+
+    def launch(self, cap, lst_ptr, n_list, n_steps, stream, uniforms=None):
+        d = self._desc(cap, None, n_list, uniforms)
+        d.list = lst_ptr
+        _lib.check(_lib.lib().pyqmd_ensemble_step(C.byref(d), n_steps, stream), "pyqmd_ensemble_step")
+
+    def step(self, n_steps=1, uniforms=None):
+        """``n_steps`` sub-steps of every nucleus (nuclear_sim.py:161-173).  ``uniforms``:
+        optional float64 tensor [n_steps, n_nuclei, 4] of draws (slots of SURVEY.md section 8a)
+        replacing the Philox stream -- the bit-exact parity path."""
+        if uniforms is not None:
+            uniforms = torch.as_tensor(uniforms, dtype=torch.float64).contiguous().to(self.device)
+            assert tuple(uniforms.shape) == (n_steps, self.n_nuclei, 4)
+        lib = _lib.lib()
+        stream = _lib.current_stream()
+        for cap, lst, n_list in self.bins:
+            d = self._desc(cap, lst, n_list, uniforms)
+            _lib.check(lib.pyqmd_ensemble_step(C.byref(d), n_steps, stream), "pyqmd_ensemble_step")
+        self.step_index += n_steps
+        return len(self.bins)
+
+    def pairs_per_step(self):
+        """Ordered pair interactions one sub-step evaluates: sum of A(A-1)."""
+        c = self.count.to(torch.int64)
+        return int((c * (c - 1)).sum().item())
+
+    def events(self):
+        """Decay events so far as a structured numpy array sorted by (step, nucleus)."""
+        n = min(int(self.event_count.item()), self.event_capacity)
+        raw = self.events_buf[: n * _lib.EVENT_DTYPE.itemsize].cpu().numpy()
+        ev = raw.view(_lib.EVENT_DTYPE).copy()
+        return ev[np.lexsort((ev["nucleus"], ev["step"]))]
+
+    def to_host(self):
+        return dict(pos=self.pos.cpu().numpy(), vel=self.vel.cpu().numpy(),
+                    is_proton=self.is_proton.cpu().numpy(), offsets=self.offsets.cpu().numpy(),
+                    count=self.count.cpu().numpy(), zn=self.zn.cpu().numpy(),
+                    half_life=self.half_life.cpu().numpy(), p_decay=self.p_decay.cpu().numpy(),
+                    mode_counts=self.mode_counts.cpu().numpy())
+
+
+# =================================================================================================
+class HostEnsembleRunner:
+    """End-to-end path with HOST-resident state, the shape of the reference's per-step call
+    (nuclear_forces.py:190-234: pack -> H2D -> kernel -> D2H -> write back): the ensemble lives in
+    pinned host memory; every ``step`` uploads it, runs the sub-steps and downloads it again.
+    The nuclei are cut into chunks that flow through a few CUDA streams, so the upload of chunk
+    k+1, the kernel of chunk k and the download of chunk k-1 overlap."""
+
+    def __init__(self, ens: NucleusEnsemble, chunks=8, n_streams=4):
+        self.ens = ens
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        self.h_pos, self.h_vel, self.h_isp = pin(ens.pos), pin(ens.vel), pin(ens.is_proton)
+        self.h_count, self.h_zn = pin(ens.count), pin(ens.zn)
+        off = ens.offsets.cpu().numpy()
+        cnt = ens.count.cpu().numpy()
+        n = ens.n_nuclei
+        chunks = max(1, min(chunks, n))
+        bounds = [round(k * n / chunks) for k in range(chunks + 1)]
+        dev = ens.device
+        self.lists = []
+        for cap, lst, n_list in ens.bins:
+            idx = (np.arange(n, dtype=np.int32) if lst is None else lst.cpu().numpy())
+            self.lists.append((cap, torch.from_numpy(idx).to(dev), idx))
+        self.chunks = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if b <= a:
+                continue
+            s0 = int(off[a])
+            s1 = int(off[b - 1] + cnt[b - 1])
+            launches = []
+            for cap, lst_dev, idx in self.lists:
+                lo, hi = np.searchsorted(idx, a), np.searchsorted(idx, b)
+                if hi > lo:
+                    launches.append((cap, lst_dev.data_ptr() + 4 * int(lo), int(hi - lo)))
+            self.chunks.append((a, b, s0, s1, launches))
+        self.n_chunks = len(self.chunks)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, self.n_chunks))]
+        self.h2d_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes + self.h_isp.nbytes)
+        self.d2h_bytes = int(self.h2d_bytes + self.h_count.nbytes + self.h_zn.nbytes)
+
+    def step(self, n_steps=1):
+        ens = self.ens
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+        for k, (a, b, s0, s1, launches) in enumerate(self.chunks):
+            st = self.streams[k % len(self.streams)]
+            with torch.cuda.stream(st):
+                ens.pos[s0:s1].copy_(self.h_pos[s0:s1], non_blocking=True)
+                ens.vel[s0:s1].copy_(self.h_vel[s0:s1], non_blocking=True)
+                ens.is_proton[s0:s1].copy_(self.h_isp[s0:s1], non_blocking=True)
+                for cap, lst_ptr, n_list in launches:
+                    ens.launch(cap, lst_ptr, n_list, n_steps, st.cuda_stream)
+                self.h_pos[s0:s1].copy_(ens.pos[s0:s1], non_blocking=True)
+                self.h_vel[s0:s1].copy_(ens.vel[s0:s1], non_blocking=True)
+                self.h_isp[s0:s1].copy_(ens.is_proton[s0:s1], non_blocking=True)
+                self.h_count[a:b].copy_(ens.count[a:b], non_blocking=True)
+                self.h_zn[a:b].copy_(ens.zn[a:b], non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        ens.step_index += n_steps
+
+
+# =================================================================================================
+class NucleonCloud:
+    """One N-nucleon system; rank ``rank`` of ``world`` owns the i-block [i0, i1) and every rank
+    holds a full replica of the positions, refreshed by an all-gather after each step."""
+
+    def __init__(self, pos, is_proton, vel=None, *, device="cuda", dt=DEFAULT_DT,
+                 strengths=DEFAULT_STRENGTHS, rank=0, world=1, group=None, sort=True,
+                 keep_force=False):
+        _lib.require_cuda()
+        dev = self.device = torch.device(device)
+        pos = torch.as_tensor(pos, dtype=torch.float32).reshape(-1, 2).to(dev)
+        isp = torch.as_tensor(is_proton, dtype=torch.uint8).to(dev)
+        vel = torch.zeros_like(pos) if vel is None else torch.as_tensor(
+            vel, dtype=torch.float32).reshape(-1, 2).to(dev)
+        self.n = int(pos.shape[0])
+        self.dt, self.strengths = float(dt), tuple(float(s) for s in strengths)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.chunk = (self.n + self.world - 1) // self.world
+        self.i0 = min(self.rank * self.chunk, self.n)
+        self.i1 = min(self.i0 + self.chunk, self.n)
+        self.perm = None
+        if sort and self.n > 0:
+            self.perm = self._sort_perm(pos, isp)
+            pos, vel, isp = pos[self.perm].contiguous(), vel[self.perm].contiguous(), isp[self.perm].contiguous()
+        padded = self.chunk * self.world
+        self.pos = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
+        self.pos_next = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
+        self.pos[: self.n] = pos
+        self.vel = vel.contiguous()
+        self.is_proton = isp.contiguous()
+        self.force = torch.zeros(self.n, 2, device=dev, dtype=torch.float32) if keep_force else None
+        ws = int(_lib.lib().pyqmd_cloud_workspace_bytes(self.n))
+        self.workspace = torch.zeros(max(ws, 64), dtype=torch.uint8, device=dev)
+        self.steps_done = 0
+
+    def _sort_perm(self, pos, isp):
+        lo = pos.min(0).values
+        extent = float((pos.max(0).values - lo).max().item()) * 1.0001 + 1e-6
+        keys = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().pyqmd_cloud_sort_keys(
+            pos.contiguous().data_ptr(), isp.data_ptr(), self.n, float(lo[0]), float(lo[1]),
+            extent, keys.data_ptr(), _lib.current_stream()), "pyqmd_cloud_sort_keys")
+        return torch.argsort(keys)
+
+    def step(self, n_steps=1):
+        lib = _lib.lib()
+        S, Cc, P = self.strengths
+        for _ in range(n_steps):
+            _lib.check(lib.pyqmd_cloud_step(
+                self.pos.data_ptr(), self.pos_next.data_ptr(), self.vel.data_ptr(),
+                _lib.ptr(self.force), self.is_proton.data_ptr(), self.n, self.i0, self.i1, S, Cc,
+                P, self.dt, self.workspace.data_ptr(), _lib.current_stream()), "pyqmd_cloud_step")
+            if self.world > 1:
+                import torch.distributed as dist
+                mine = self.pos_next[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+                dist.all_gather_into_tensor(self.pos_next, mine, group=self.group)
+            self.pos, self.pos_next = self.pos_next, self.pos
+            self.steps_done += 1
+
+    def pairs_per_step(self):
+        """Ordered pairs this rank evaluates per step: (i1 - i0) * (n - 1)."""
+        return (self.i1 - self.i0) * (self.n - 1)
+
+    def _unsort(self, t):
+        if self.perm is None:
+            return t
+        out = torch.empty_like(t)
+        out[self.perm] = t
+        return out
+
+    def positions(self):
+        """Positions in the caller's original nucleon order."""
+        return self._unsort(self.pos[: self.n])
+
+    def velocities(self):
+        return self._unsort(self.vel)
+
+    def forces(self):
+        return None if self.force is None else self._unsort(self.force)
+
+
+# =================================================================================================
+class DecayPopulation:
+    """Particle-less nuclei: per sub-step should_decay (decay_chains.py:400-421) and, on a hit,
+    the (Z, N) / half-life update of handle_decay (nuclear_sim.py:213,288-289,353)."""
+
+    def __init__(self, zn, *, device="cuda", dt_decay, seed=0, id_base=0, watch=(),
+                 half_life=None, p_decay=None, init_seed=0):
+        _lib.require_cuda()
+        dev = self.device = torch.device(device)
+        self.zn = torch.as_tensor(zn, dtype=torch.int32).contiguous().to(dev)
+        self.n = int(self.zn.numel())
+        self.dt_decay, self.seed, self.id_base = float(dt_decay), int(seed), int(id_base)
+        if half_life is None or p_decay is None:
+            uniq, inv = torch.unique(self.zn, return_inverse=True)
+            Tu, pu = initial_half_lives(uniq.cpu().numpy(), self.dt_decay,
+                                        np.random.default_rng(init_seed))
+            kinds = [nuclides.half_life_class(*nuclides.zn_unpack(v))[0] for v in uniq.tolist()]
+            if any(k == _lib.HL_BAND for k in kinds):
+                T, p = initial_half_lives(self.zn.cpu().numpy(), self.dt_decay,
+                                          np.random.default_rng(init_seed))
+                half_life, p_decay = torch.from_numpy(T), torch.from_numpy(p)
+            else:
+                half_life = torch.from_numpy(Tu).to(dev)[inv]
+                p_decay = torch.from_numpy(pu).to(dev)[inv]
+        self.half_life = torch.as_tensor(half_life, dtype=torch.float64).contiguous().to(dev)
+        self.p_decay = torch.as_tensor(p_decay, dtype=torch.float64).contiguous().to(dev)
+        self.table = device_table(self.dt_decay, dev)
+        self.watch = [nuclides.zn_pack(z, n) for z, n in watch][:8]
+        self.step_index = 0
+
+    def step(self, n_steps=1, uniforms=None, want_decisions=False):
+        """Returns (counts[n_steps, 16] int64 tensor, decisions[n_steps, n] uint8 or None);
+        counts columns: decays by DecayType value 0..7, then decays of watch[k] in 8..15."""
+        dev = self.device
+        counts = torch.zeros(n_steps, _lib.COUNT_COLS, dtype=torch.int64, device=dev)
+        decided = torch.zeros(n_steps, self.n, dtype=torch.uint8, device=dev) if want_decisions else None
+        if uniforms is not None:
+            uniforms = torch.as_tensor(uniforms, dtype=torch.float64).contiguous().to(dev)
+            assert tuple(uniforms.shape) == (n_steps, self.n, 4)
+        d = _lib.PopulationDesc()
+        d.zn, d.half_life, d.p_decay = self.zn.data_ptr(), self.half_life.data_ptr(), self.p_decay.data_ptr()
+        d.n, d.id_base, d.table, d.dt_decay = self.n, self.id_base, self.table.data_ptr(), self.dt_decay
+        d.uniforms, d.uniforms_n = _lib.ptr(uniforms), self.n
+        d.seed, d.step0, d.n_watch = self.seed, self.step_index, len(self.watch)
+        for k, v in enumerate(self.watch):
+            d.watch_zn[k] = v
+        d.step_counts, d.decided = counts.data_ptr(), _lib.ptr(decided)
+        _lib.check(_lib.lib().pyqmd_population_step(C.byref(d), n_steps, _lib.current_stream()),
+                   "pyqmd_population_step")
+        self.step_index += n_steps
+        return counts, decided

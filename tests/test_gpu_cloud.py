@@ -1,0 +1,166 @@
+"""GPU parity of the single-cloud path (BASELINE config 4) against the oracle, through
+pyqmd_cloud_step / pyqmd_cloud_sort_keys."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import FORCE_TOL, POS_TOL, extent_of
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cloud(n, seed=1234, frac_p=0.4, density=1 / 25):
+    """i.i.d. uniform in a disc of number density 1/25, exactly
+    round(frac_p * n) protons at shuffled indices, PCG64(seed)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    R = np.sqrt(n / density / np.pi)
+    r = R * np.sqrt(rng.random(n))
+    th = 2 * np.pi * rng.random(n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32)
+    isp = np.zeros(n, np.uint8)
+    isp[rng.permutation(n)[: int(round(frac_p * n))]] = 1
+    return pos, isp
+
+
+def oracle_forces(pos, isp, i0, i1, strengths=(150.0, 30.0, 35.0), amb_check=True):
+    x = pos[:, 0].astype(np.float64); y = pos[:, 1].astype(np.float64)
+    cx, cy = float(x.mean()), float(y.mean())
+    return orc.cloud_forces(x, y, isp, i0, i1, *strengths, center=(cx, cy))
+
+
+def ambiguous_mask(pos, i0, i1, tol=1e-6):
+    """Nucleons of [i0,i1) with a partner within tol (relative) of a branch threshold."""
+    p = pos.astype(np.float64)
+    out = np.zeros(i1 - i0, bool)
+    for k, i in enumerate(range(i0, i1)):
+        d = np.hypot(p[:, 0] - p[i, 0], p[:, 1] - p[i, 1])
+        d[i] = 1e9
+        for thr in (0.1, 2.8, 4.25, 8.0, 9.0):
+            if (np.abs(d - thr) <= tol * thr * 2).any():
+                out[k] = True
+    return out
+
+
+def rel_l2(a, b, mask=None):
+    if mask is not None:
+        a, b = a[~mask], b[~mask]
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+@pytest.mark.parametrize("sort", [True, False])
+def test_subcloud_4096_forces_and_step(sort):
+    from pyqmd_b200.state import NucleonCloud
+    n = 4096
+    pos, isp = make_cloud(n)
+    cloud = NucleonCloud(pos, isp, sort=sort, keep_force=True)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    fx, fy = oracle_forces(pos, isp, 0, n)
+    amb = ambiguous_mask(pos, 0, n)
+    assert amb.sum() < 20
+    Fo = np.stack([fx, fy], 1)
+    assert rel_l2(F, Fo, amb) <= FORCE_TOL
+    # one step from rest: x' = x + 0.85 F dt^2
+    dt = cloud.dt
+    want = pos.astype(np.float64) + 0.85 * Fo * dt * dt
+    got = cloud.positions().cpu().numpy().astype(np.float64)
+    err = np.hypot(*(got - want).T)[~amb].max() / extent_of(pos)
+    assert err <= POS_TOL
+    v = cloud.velocities().cpu().numpy().astype(np.float64)
+    assert rel_l2(v, 0.85 * Fo * dt, amb) <= 2e-5
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 255, 256, 257, 1023, 1024, 1025, 3000])
+def test_ragged_sizes(n):
+    """Tile (256) and i-block (1024) boundaries, partial last tile, single nucleon."""
+    from pyqmd_b200.state import NucleonCloud
+    pos, isp = make_cloud(n, seed=n)
+    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    fx, fy = oracle_forces(pos, isp, 0, n)
+    amb = ambiguous_mask(pos, 0, n)
+    Fo = np.stack([fx, fy], 1)
+    if np.abs(Fo[~amb]).max() > 0:
+        assert rel_l2(F, Fo, amb) <= FORCE_TOL
+    else:
+        assert np.abs(F[~amb]).max() == 0.0
+
+
+def test_dense_cloud_all_branches():
+    """A compressed cloud (mean spacing ~2) exercises hard core, core, attractive, Pauli and
+    the clamp in the tiled kernel's near path."""
+    from pyqmd_b200.state import NucleonCloud
+    n = 2000
+    pos, isp = make_cloud(n, seed=7, density=1 / 4)
+    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    fx, fy = oracle_forces(pos, isp, 0, n)
+    amb = ambiguous_mask(pos, 0, n)
+    assert rel_l2(F, np.stack([fx, fy], 1), amb) <= FORCE_TOL
+
+
+def test_clamped_far_path_with_large_strengths():
+    from pyqmd_b200.state import NucleonCloud
+    n = 3000
+    pos, isp = make_cloud(n, seed=9)
+    st = (20000.0, 3000.0, 35.0)          # tail + Coulomb can hit the +-12 cap beyond d = 9
+    cloud = NucleonCloud(pos, isp, keep_force=True, strengths=st)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    fx, fy = oracle_forces(pos, isp, 0, n, strengths=st)
+    amb = ambiguous_mask(pos, 0, n)
+    assert rel_l2(F, np.stack([fx, fy], 1), amb) <= FORCE_TOL
+
+
+def test_i_block_sharding_is_bit_identical():
+    """Two 'ranks' computing [0, n/2) and [n/2, n) of the same replica reproduce the single-GPU
+    step exactly (what the all-gather path relies on)."""
+    from pyqmd_b200 import _lib
+    from pyqmd_b200.state import NucleonCloud
+    n = 5000
+    pos, isp = make_cloud(n, seed=3)
+    full = NucleonCloud(pos, isp)
+    full.step(1)
+    a = NucleonCloud(pos, isp, rank=0, world=1)
+    b = NucleonCloud(pos, isp, rank=0, world=1)
+    # emulate world = 2 without a process group: restrict the i-range by hand
+    h = (n + 1) // 2
+    a.i0, a.i1 = 0, h
+    b.i0, b.i1 = h, n
+    a.step(1); b.step(1)
+    merged = torch.cat([a.pos[:h], b.pos[h:n]])
+    assert torch.equal(merged, full.pos[:n])
+
+
+def test_large_cloud_sampled_against_oracle():
+    """N = 200,000: sorted, tile-classified fast path; 384 sampled nucleons against the oracle."""
+    from pyqmd_b200.state import NucleonCloud
+    n = 200_000
+    pos, isp = make_cloud(n, seed=11)
+    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    x = pos[:, 0].astype(np.float64); y = pos[:, 1].astype(np.float64)
+    c = (float(x.mean()), float(y.mean()))
+    for i0 in (0, 77_777, n - 128):
+        fx, fy = orc.cloud_forces(x, y, isp, i0, i0 + 128, center=c)
+        amb = ambiguous_mask(pos, i0, i0 + 128)
+        assert rel_l2(F[i0:i0 + 128], np.stack([fx, fy], 1), amb) <= FORCE_TOL
+    # Newton 3 on the whole cloud: pair forces cancel, only containment remains
+    assert np.isfinite(F).all()
+
+
+def test_multi_step_cloud_teacher_forced():
+    from pyqmd_b200.state import NucleonCloud
+    n = 1500
+    pos, isp = make_cloud(n, seed=21, density=1 / 9)
+    cloud = NucleonCloud(pos, isp, keep_force=True, sort=False)
+    for s in range(4):
+        p0 = cloud.pos[:n].cpu().numpy().copy()
+        cloud.step(1)
+        fx, fy = oracle_forces(p0, isp, 0, n)
+        amb = ambiguous_mask(p0, 0, n)
+        assert rel_l2(cloud.force.cpu().numpy().astype(np.float64), np.stack([fx, fy], 1), amb) <= FORCE_TOL

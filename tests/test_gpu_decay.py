@@ -1,0 +1,268 @@
+"""GPU parity of the stochastic decay path: decisions must be BIT-EXACT given the same uniform
+draws (north star), through pyqmd_population_step / pyqmd_ensemble_step."""
+import math
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import unhex
+from gpu_util import POS_TOL, oracle_step, pos_error
+from oracle import decay_oracle as dor
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+C14, U238 = (6, 8), (92, 146)
+
+
+def zn(z, n):
+    return (z << 16) | n
+
+
+def test_decisions_bit_exact_mt19937_stream(decay_events):
+    """random.seed(12345), C-14, dt = 0.1 T -> the reference's decision string."""
+    from pyqmd_b200.state import DecayPopulation
+    for row in decay_events["seeded"]:
+        T, dt = float.fromhex(row["T"]), float.fromhex(row["dt"])
+        u = unhex(row["uniforms"])
+        k = len(u)
+        # one nucleus per draw, one step, so daughters never matter
+        pop = DecayPopulation(np.full(k, zn(row["z"], row["n"]), np.int32), dt_decay=dt)
+        assert float(pop.half_life[0]) == T
+        uni = np.zeros((1, k, 4)); uni[0, :, 0] = u; uni[0, :, 1:] = 0.5
+        _, dec = pop.step(1, uniforms=uni, want_decisions=True)
+        bits = "".join("1" if b else "0" for b in dec[0].cpu().numpy())
+        assert bits == row["bits"]
+
+
+@pytest.mark.parametrize("frac", [1e-3, 0.1, 1.0, 50.0])
+def test_million_nuclei_32_steps_bit_exact(frac):
+    """10^6 nuclei x 32 steps (C-14 and U-238 halves) with shared uniforms: every decision equals
+    the oracle's [u < p]; daughters are followed exactly like handle_decay would."""
+    from pyqmd_b200.state import DecayPopulation
+    n, steps = 1_000_000, 32
+    znv = np.where(np.arange(n) % 2 == 0, zn(*C14), zn(*U238)).astype(np.int32)
+    Tc = dor.half_life(*C14)[0]
+    dt = frac * Tc
+    rng = np.random.default_rng(12345)
+    pop = DecayPopulation(znv, dt_decay=dt)
+    fired_total = 0
+    # oracle side: parents only decide once with p(parent); after a decay the daughter's p applies
+    T = np.where(np.arange(n) % 2 == 0, Tc, dor.half_life(*U238)[0])
+    cur_z = np.where(np.arange(n) % 2 == 0, 6, 92); cur_n = np.where(np.arange(n) % 2 == 0, 8, 146)
+    for s0 in range(0, steps, 8):
+        uni = rng.random((8, n, 4))
+        _, dec = pop.step(8, uniforms=uni, want_decisions=True)
+        dec = dec.cpu().numpy().astype(bool)
+        for s in range(8):
+            want, consumed = orc.decay_decisions(T, dt, uni[s, :, 0])
+            assert np.array_equal(dec[s], want), (s0 + s)
+            for k in np.nonzero(want)[0]:
+                nz, nn, mode, _ = dor.decay_product(int(cur_z[k]), int(cur_n[k]), uni[s, k, 1])
+                if mode is None:
+                    continue
+                cur_z[k], cur_n[k] = nz, nn
+                T[k] = dor.half_life(nz, nn, uni[s, k, 3])[0]
+            fired_total += int(want.sum())
+    got_zn = pop.zn.cpu().numpy()
+    assert np.array_equal(got_zn, (cur_z << 16) | cur_n)
+    gT = pop.half_life.cpu().numpy()
+    fin = np.isfinite(T)
+    assert np.array_equal(np.isfinite(gT), fin)
+    assert np.allclose(gT[fin], T[fin], rtol=4e-16, atol=0)      # band estimates: CUDA pow vs glibc
+    assert fired_total > 0 or frac < 1e-2
+
+
+def test_philox_stream_matches_oracle_and_is_shard_invariant():
+    """In-kernel RNG: decisions equal [philox_u53(seed, id, step, 0) < p] from the oracle's
+    Philox4x32-10, and do not depend on how the population is split (id_base)."""
+    from pyqmd_b200.state import DecayPopulation
+    n, seed = 50_000, 0xC0FFEE1234
+    Tc = dor.half_life(*C14)[0]
+    dt = 0.3 * Tc
+    znv = np.full(n, zn(*C14), np.int32)
+    one = DecayPopulation(znv, dt_decay=dt, seed=seed)
+    _, d_one = one.step(1, want_decisions=True)
+    p = orc.decay_probability(Tc, dt)
+    want = orc.philox_uniforms(seed, 0, n, 0, 0) < p
+    assert np.array_equal(d_one[0].cpu().numpy().astype(bool), want)
+    h = n // 2
+    a = DecayPopulation(znv[:h], dt_decay=dt, seed=seed, id_base=0)
+    b = DecayPopulation(znv[h:], dt_decay=dt, seed=seed, id_base=h)
+    _, da = a.step(1, want_decisions=True); _, db = b.step(1, want_decisions=True)
+    assert torch.equal(torch.cat([da[0], db[0]]), d_one[0])
+    # second step uses counter step = 1
+    _, d2 = one.step(1, want_decisions=True)
+    alive = ~want
+    want2 = (orc.philox_uniforms(seed, 0, n, 1, 0) < p) & alive      # N-14 daughters are stable
+    assert np.array_equal(d2[0].cpu().numpy().astype(bool), want2)
+
+
+def test_half_life_statistics_config5():
+    """Config C5 (scaled to 2x10^7 nuclei): survivors per step follow the reference's effective
+    law N0 (1-p)^k (4 sigma), which sits 9.3e-5 (relative rate) off the analytic 0.5^(t/T)
+    because the reference uses 0.693 for ln 2 (particles.py:140)."""
+    from pyqmd_b200.state import DecayPopulation
+    n = 20_000_000
+    znv = torch.full((n,), zn(*C14), dtype=torch.int32)
+    znv[n // 2:] = zn(*U238)
+    Tc, Tu = dor.half_life(*C14)[0], dor.half_life(*U238)[0]
+    steps = 200
+    for (T, watch_col) in ((Tc, 8), (Tu, 9)):
+        dt = T / 1000.0
+        pop = DecayPopulation(znv, dt_decay=dt, seed=99, watch=(C14, U238))
+        counts, _ = pop.step(steps)
+        dec = counts[:, watch_col].cpu().numpy().astype(np.float64)
+        n0 = n // 2
+        surv = n0 - np.cumsum(dec)
+        p = orc.decay_probability(T, dt)
+        assert p.hex() == "0x1.6b54e2b063e07p-11"
+        k = np.arange(1, steps + 1)
+        expect = n0 * (1 - p) ** k
+        sigma = np.sqrt(n0 * (1 - (1 - p) ** k) * (1 - p) ** k)
+        assert np.all(np.abs(surv - expect) <= 4.5 * sigma + 1)
+        analytic = n0 * 0.5 ** (k * dt / T)
+        rel = (expect[-1] - analytic[-1]) / (n0 - analytic[-1])
+        assert abs(rel - (-2.1e-4)) < 1.5e-4        # 0.693 vs ln 2 bias of the decay rate
+
+
+def _device_nucleus(rec, dt_decay, **kw):
+    from pyqmd_b200.state import NucleusEnsemble
+    x, y = unhex(rec["x"]), unhex(rec["y"])
+    pos = np.stack([x, y], 1).astype(np.float32)
+    vel = np.stack([unhex(rec["vx"]), unhex(rec["vy"])], 1).astype(np.float32)
+    isp = np.array(rec["is_proton"], np.uint8)
+    T = float.fromhex(rec["T"])
+    from pyqmd_b200 import nuclides
+    return NucleusEnsemble(np.array([zn(rec["z"], rec["n"])], np.int32), np.array([0], np.int64),
+                           np.array([len(isp)], np.int32), pos, vel, isp, dt_decay=dt_decay,
+                           half_life=np.array([T]),
+                           p_decay=np.array([nuclides.decay_probability(T, dt_decay)]), **kw)
+
+
+def test_substep_loops_against_reference_goldens(decay_events):
+    """decay test -> handle_decay slice -> force step (nuclear_sim.py:165-173) on the device with
+    the golden draws: Z, N, nucleon types/count and decisions exact; half-life exact when it
+    comes from the table; positions within the per-step tolerance."""
+    for loop in decay_events["loops"]:
+        dt_decay, dt_phys = float.fromhex(loop["dt_decay"]), float.fromhex(loop["dt_phys"])
+        ens = _device_nucleus(loop["start"], dt_decay, dt_phys=dt_phys)
+        onuc = None
+        for k, st in enumerate(loop["steps"]):
+            draws = [float.fromhex(h) for h in st["draws"]]
+            # golden draws are a stream (slot0 | branch?, angle?, half-life?) -> slot layout
+            cnt = int(ens.count[0]); z_, n_ = int(ens.zn[0]) >> 16, int(ens.zn[0]) & 0xffff
+            p = float(ens.p_decay[0])
+            slots = [draws[0], 0.5, 0.5, 0.5]
+            seq = draws[1:]
+            if p >= 0 and draws[0] < p:
+                opts = dor.decay_options(z_, n_)
+                if len(opts) > 1:
+                    slots[1] = seq.pop(0)
+                mode_pre = opts[dor.pick_option(opts, slots[1])][2]
+                if mode_pre in dor.EMISSION:
+                    slots[2] = seq.pop(0)
+                if seq:
+                    slots[3] = seq.pop(0)
+            p0 = ens.pos[:cnt].cpu().numpy().copy(); v0 = ens.vel[:cnt].cpu().numpy().copy()
+            isp0 = ens.is_proton[:cnt].cpu().numpy().copy()
+            ens.step(1, uniforms=np.array(slots).reshape(1, 1, 4))
+            after = st["after"]
+            cnt1 = int(ens.count[0])
+            assert (int(ens.zn[0]) >> 16, int(ens.zn[0]) & 0xffff) == (after["z"], after["n"]), (loop["z"], k)
+            assert cnt1 == len(after["is_proton"])
+            assert ens.is_proton[:cnt1].cpu().numpy().tolist() == after["is_proton"]
+            Tw = float.fromhex(after["T"])
+            Tg = float(ens.half_life[0])
+            assert Tg == Tw or abs(Tg - Tw) <= 4e-16 * abs(Tw), (loop["z"], k, Tg, Tw)
+            # positions: oracle from the device's own pre-step state (teacher forced)
+            onuc = dor.OracleNucleus(z_, n_, p0[:, 0], p0[:, 1], isp0, v0[:, 0], v0[:, 1], T=1.0)
+            onuc.T = float.fromhex(loop["start"]["T"]) if k == 0 else onuc.T
+            if st["decayed"] and st["mode"] != -1:
+                onuc.z, onuc.n = z_, n_
+                onuc.decay_event(slots[1], slots[2], slots[3])
+            if len(onuc.x):
+                pos32 = np.stack([onuc.x, onuc.y], 1).astype(np.float32)
+                vel32 = np.stack([onuc.vx, onuc.vy], 1).astype(np.float32)
+                tp = np.array([1 if t == dor.PROTON else 0 for t in onuc.types], np.uint8)
+                ox, oy, _, _, _, _, amb = oracle_step(pos32, vel32, tp, dt_phys)
+                assert pos_error(pos32, ens.pos[:cnt1].cpu().numpy(), ox, oy, amb) <= POS_TOL
+        ev = ens.events()
+        n_dec = sum(1 for s in loop["steps"] if s["decayed"] and s["mode"] != -1)
+        assert len(ev) == n_dec
+
+
+def test_chain_walk_events_on_device(decay_events):
+    """Forced decays (p = 1) down the golden chains: daughters, particle bookkeeping and the
+    emitted particle (type, direction, speed) against the reference's records."""
+    for walk in decay_events["walks"]:
+        rec = walk["start"]
+        ens = _device_nucleus(rec, 1.0)
+        for k, ev in enumerate(walk["events"]):
+            draws = [float.fromhex(h) for h in ev["draws"]]
+            z_, n_ = int(ens.zn[0]) >> 16, int(ens.zn[0]) & 0xffff
+            slots = [0.0, 0.5, 0.5, 0.5]
+            seq = list(draws)
+            opts = dor.decay_options(z_, n_)
+            if len(opts) > 1:
+                slots[1] = seq.pop(0)
+            mode_pre = opts[dor.pick_option(opts, slots[1])][2]
+            if mode_pre in dor.EMISSION:
+                slots[2] = seq.pop(0)
+            if seq:
+                slots[3] = seq.pop(0)
+            ens.p_decay[0] = 1.0                 # force the decision (SPACE key, nuclear_sim.py:433)
+            ens.dt_phys = 0.0                    # isolate the decay slice: no motion
+            n_before = len(ens.events())
+            ens.step(1, uniforms=np.array(slots).reshape(1, 1, 4))
+            after = ev["after"]
+            cnt1 = int(ens.count[0])
+            assert (int(ens.zn[0]) >> 16, int(ens.zn[0]) & 0xffff) == (after["z"], after["n"])
+            assert ens.is_proton[:cnt1].cpu().numpy().tolist() == after["is_proton"]
+            evs = ens.events()
+            if ev["mode"] == -1:
+                assert len(evs) == n_before
+                continue
+            assert len(evs) == n_before + 1
+            e = evs[-1]
+            assert e["mode"] == ev["mode"] and e["zn_new"] == zn(after["z"], after["n"])
+            if ev["emitted"]:
+                ptype, x, y, vx, vy = ev["emitted"][0]
+                assert e["ptype"] == ptype
+                assert abs(e["vx"] - float.fromhex(vx)) <= 1e-12 * 200
+                assert abs(e["vy"] - float.fromhex(vy)) <= 1e-12 * 200
+                # emission point = centre of mass of the (FP32) survivors
+                assert abs(e["x"] - float.fromhex(x)) <= 1e-5 and abs(e["y"] - float.fromhex(y)) <= 1e-5
+            Tw, Tg = float.fromhex(after["T"]), float(ens.half_life[0])
+            assert Tg == Tw or abs(Tg - Tw) <= 4e-16 * abs(Tw)
+            # velocities were damped by 0.8 exactly where the reference does
+            wvx = unhex(after["vx"]).astype(np.float32)
+            assert np.allclose(ens.vel[:cnt1, 0].cpu().numpy(), wvx, rtol=1e-6, atol=1e-7)
+
+
+def test_mixed_ensemble_decay_statistics_and_sharding():
+    """Code-list isotopes (nuclear_sim.py:494-504) with decay on: results are identical whether
+    the ensemble runs as one piece or as two shards with id_base offsets (no communication)."""
+    from pyqmd_b200.state import CODE_ISOTOPES, NucleusEnsemble
+    n = 9 * 64
+    T_c14 = dor.half_life(*C14)[0]
+    kw = dict(dt_decay=T_c14 * 0.05, seed=4242)
+    whole = NucleusEnsemble.from_templates(CODE_ISOTOPES, n, **kw)
+    whole.step(6)
+    h = 9 * 30
+    a = NucleusEnsemble.from_templates(CODE_ISOTOPES, h, id_base=0, **kw)
+    b = NucleusEnsemble.from_templates(CODE_ISOTOPES, n - h, id_base=h, **kw)
+    a.step(6); b.step(6)
+    assert torch.equal(torch.cat([a.zn, b.zn]), whole.zn)
+    assert torch.equal(torch.cat([a.count, b.count]), whole.count)
+    assert torch.equal(a.mode_counts + b.mode_counts, whole.mode_counts)
+    assert int(whole.mode_counts.sum()) > 0
+    ev = whole.events()
+    assert len(ev) == int(whole.mode_counts.sum())
+    # live nucleons of shard a equal the same nuclei in the whole run, bit for bit
+    for k in (0, 8, 100, h - 1):
+        o, c = int(a.offsets[k]), int(a.count[k])
+        ow = int(whole.offsets[k])
+        assert torch.equal(a.pos[o:o + c], whole.pos[ow:ow + c])
