@@ -47,8 +47,8 @@ N_DECAY = 100_000_000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "mixed", "cloud", "decay"])
     ap.add_argument("--no-extras", action="store_true")

@@ -83,8 +83,10 @@ static inline int near_thr(double v, double thr, double tol)
  *   S,C,P      strong/coulomb/pauli strengths (nuclear_forces.py:13-15)
  *   fx,fy      optional out: the force on each nucleon *before* integration
  *   amb        optional out: 1 where nucleon i has a pair (or its containment test) within
- *              relative amb_tol of a branch threshold, i.e. where an FP32 evaluation may
- *              legitimately take the other branch ("hard parts")
+ *              relative amb_tol of a discontinuous branch threshold (d2 = 0.01, d = 2.8, 4.25,
+ *              8, 9; containment radius), i.e. where an FP32 evaluation may legitimately take
+ *              the other branch ("hard parts"); the +-12 clamp is
+ *              continuous and is not flagged
  *   st         optional out: branch statistics
  *   integrate  0 = compute forces only, leave state untouched
  */
@@ -154,7 +156,6 @@ void orc_force_step(int64_t n, double *x, double *y, double *vx, double *vy,
             /* :294  max(-12.0, min(12.0, net)) with Python's first-wins tie rule */
             double m = (net < 12.0) ? net : 12.0;
             double c = (m > -12.0) ? m : -12.0;
-            if (amb && (near_thr(fabs(net), 12.0, amb_tol))) a = 1;
             if (c != net) z.clamped++;
             net = c;
             if (dist > 0) {                              /* :296 */

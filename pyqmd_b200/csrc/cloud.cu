@@ -206,6 +206,9 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
     const int64_t wbase = i0 + (int64_t)blockIdx.x * kIBlock + (int64_t)wid * (32 * kIPT);
 
     float xi[kIPT], yi[kIPT], ti[kIPT], qi[kIPT], fx[kIPT], fy[kIPT];
+    // Tile-local FP32 partial sums are folded into float64 totals once per tile: with 10^5..10^6
+    // partners a single FP32 running sum loses ~sqrt(N) ulp and would break the 1e-5 budget.
+    double Fx[kIPT], Fy[kIPT];
     float bxmin = INFINITY, bymin = INFINITY, bxmax = -INFINITY, bymax = -INFINITY;
     bool allp = true, alln = true;
 #pragma unroll
@@ -219,6 +222,7 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
         ti[k] = pr ? 1.0f : 0.0f;
         qi[k] = pr ? L.C : 0.0f;
         fx[k] = 0.f; fy[k] = 0.f;
+        Fx[k] = 0.0; Fy[k] = 0.0;
         bxmin = fminf(bxmin, p.x); bxmax = fmaxf(bxmax, p.x);
         bymin = fminf(bymin, p.y); bymax = fmaxf(bymax, p.y);
         allp = allp && pr;
@@ -271,6 +275,13 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
         } else {
             near_tile(sxy, st, jmax, xi, yi, ti, fx, fy, L);
         }
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            Fx[k] += (double)fx[k];
+            Fy[k] += (double)fy[k];
+            fx[k] = 0.f;
+            fy[k] = 0.f;
+        }
     }
 
     // containment + integrate, nuclear_forces.py:301-323
@@ -285,19 +296,19 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
             // containment is part of the reported force
             const float cdx = cx - x, cdy = cy - y;
             const float cd = sqrtf(fmaf(cdy, cdy, cdx * cdx));
-            float Fx = fx[k], Fy = fy[k];
+            float Ftx = (float)Fx[k], Fty = (float)Fy[k];
             if (cd > R * 1.5f && cd > 0.01f) {
                 const float cf = 0.03f * (cd - R) / cd;
-                Fx = fmaf(cf, cdx, Fx);
-                Fy = fmaf(cf, cdy, Fy);
+                Ftx = fmaf(cf, cdx, Ftx);
+                Fty = fmaf(cf, cdy, Fty);
             }
-            v.x = fmaf(Fx, dt, v.x) * kDamp;
-            v.y = fmaf(Fy, dt, v.y) * kDamp;
+            v.x = fmaf(Ftx, dt, v.x) * kDamp;
+            v.y = fmaf(Fty, dt, v.y) * kDamp;
             x = fmaf(v.x, dt, x);
             y = fmaf(v.y, dt, y);
             pos_out[i] = make_float2(x, y);
             vel[i] = v;
-            if (force) force[i] = make_float2(Fx, Fy);
+            if (force) force[i] = make_float2(Ftx, Fty);
         }
     }
 }

@@ -73,7 +73,7 @@ def test_gpu_method_keeps_float32_attribute_types():
     ps = [Particle(400.0, 400.0, ParticleType.PROTON), Particle(403.0, 400.0, ParticleType.PROTON)]
     NuclearForces().update_particles_gpu(ps, 1 / 240)
     assert isinstance(ps[0].x, np.float32) and isinstance(ps[1].vx, np.float32)
-    assert ps[0].vx < 0 < ps[1].vx                           # p-p at d=3: net repulsion
+    assert ps[0].vx > 0 > ps[1].vx                           # p-p at d=3: net attraction (KAT-A)
 
 
 def test_u238_teacher_forced_1000_steps(u238_traj):
