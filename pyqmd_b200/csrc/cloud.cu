@@ -33,9 +33,31 @@ struct CloudWorkspace {
     float4* bbox;     // [n_tiles] xmin, ymin, xmax, ymax
     double2* sums;    // [n_tiles] partial coordinate sums
     int* flags;       // [n_tiles] kTileAll*
+    double2* partial; // [n_seg][i1 - i0] per-segment partial forces
 };
 
+constexpr int64_t kTargetUnits = 8192;   // ~28 work units per resident-block slot (148 SMs x 2)
+constexpr int kMaxSeg = 64;
+
+// number of j segments for an i-range of n_i nucleons of an n-nucleon cloud
+__host__ inline int segments_for(int64_t n, int64_t n_i)
+{
+    const int64_t iblocks = (n_i + kIBlock - 1) / kIBlock;
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    int64_t s = (kTargetUnits + iblocks - 1) / (iblocks > 0 ? iblocks : 1);
+    if (s > kMaxSeg) s = kMaxSeg;
+    if (s > tiles) s = tiles;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
 __host__ __device__ inline int64_t n_tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
+
+static int64_t partial_entries(int64_t n)
+{
+    // worst case over all i-ranges [i0, i1) of an n-nucleon cloud of n_seg * (i1 - i0)
+    return n + (kTargetUnits + kMaxSeg) * (int64_t)kIBlock;
+}
 
 static CloudWorkspace carve(void* ws, int64_t n)
 {
@@ -45,7 +67,8 @@ static CloudWorkspace carve(void* ws, int64_t n)
     w.centre = reinterpret_cast<double*>(p);            p += 32;
     w.bbox = reinterpret_cast<float4*>(p);              p += sizeof(float4) * nt;
     w.sums = reinterpret_cast<double2*>(p);             p += sizeof(double2) * nt;
-    w.flags = reinterpret_cast<int*>(p);
+    w.flags = reinterpret_cast<int*>(p);              p += (sizeof(int) * nt + 255) / 256 * 256;
+    w.partial = reinterpret_cast<double2*>(p);
     return w;
 }
 
@@ -122,69 +145,169 @@ __global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_
     }
 }
 
-// ---- pass 3: forces + integrate ----------------------------------------------------------------
-template <int MODE /*0 none, 1 all p-p, 2 per-pair charge*/, bool CLAMP>
-__device__ __forceinline__ void far_tile(const float2* __restrict__ sxy, const float* __restrict__ st,
-                                         int jmax, const float (&xi)[kIPT], const float (&yi)[kIPT],
-                                         const float (&qi)[kIPT], float (&fx)[kIPT],
-                                         float (&fy)[kIPT], const LawParams& L)
+// ---- pass 3: partial forces of one work unit = (i-block, j-segment) --------------------------------
+//
+// Packed FP32 (Blackwell add/mul/fma.f32x2 -> FADD2/FMUL2/FFMA2): one instruction works on two
+// pairs, so the 14 FMA-pipe operations of a far pair cost 7 issue slots instead of 14 and the
+// kernel moves from issue-bound (ncu r01a: 82 % issue, 18 instr/pair) towards the MUFU limit of
+// 2 special-function ops per pair.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi)
 {
-    const float4* s4 = reinterpret_cast<const float4*>(sxy);
-    const int pairs = jmax >> 1;
-#pragma unroll 2
-    for (int jj = 0; jj < pairs; ++jj) {
-        const float4 o = s4[jj];
-        float t0 = 0.f, t1 = 0.f;
-        if (MODE == 2) { t0 = st[2 * jj]; t1 = st[2 * jj + 1]; }
+    f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+struct FarConsts {
+    f32x2 kexp, logA, c3, c2, c1, one, e2, ne, negC;
+};
+
+__device__ __forceinline__ FarConsts make_far_consts(const LawParams& L)
+{
+    FarConsts c;
+    const float k = -1.8f * kLog2e / 7.0f;
+    c.kexp = pk(k, k);
+    c.logA = pk(L.log2TailK, L.log2TailK);
+    c.c3 = pk(-kEps * kEps * kEps, -kEps * kEps * kEps);
+    c.c2 = pk(kEps * kEps, kEps * kEps);
+    c.c1 = pk(-kEps, -kEps);
+    c.one = pk(1.0f, 1.0f);
+    c.e2 = pk(kEps * kEps, kEps * kEps);
+    c.ne = pk(-kEps, -kEps);
+    c.negC = pk(-L.C, -L.C);
+    return c;
+}
+
+// Two far pairs (one i, two j) in packed form; same arithmetic as pair_far_impl<MODE,false>.
+template <int MODE>
+__device__ __forceinline__ void far_pair2(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
+                                          const FarConsts& c, f32x2& fx, f32x2& fy)
+{
+    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
+    const f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
+    float a0, a1;
+    upk(d2, a0, a1);
+    const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
+    const f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
+    upk(arg, a0, a1);
+    const f32x2 e = pk(mufu_ex2(a0), mufu_ex2(a1));
+    f32x2 h = fma2(r, c.c3, c.c2);
+    h = fma2(r, h, c.c1);
+    h = fma2(r, h, c.one);
+    const f32x2 r2 = mul2(r, r);
+    f32x2 s = mul2(e, mul2(h, r2));
+    if (MODE != 0) {
+        f32x2 g = fma2(r2, c.e2, c.ne);
+        g = fma2(r2, g, c.one);
+        const f32x2 q = (MODE == 1) ? c.negC : cq;          // cq already carries the minus sign
+        s = fma2(mul2(q, r), mul2(g, r2), s);
+    }
+    fx = fma2(dx, s, fx);
+    fy = fma2(dy, s, fy);
+}
+
+template <int MODE>
+__device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
+                                                const float* __restrict__ sy,
+                                                const float* __restrict__ st, int jmax,
+                                                const float (&xi)[kIPT], const float (&yi)[kIPT],
+                                                const float (&qi)[kIPT], float (&fx)[kIPT],
+                                                float (&fy)[kIPT], const LawParams& L)
+{
+    const FarConsts c = make_far_consts(L);
+    f32x2 xi2[kIPT], yi2[kIPT], nq2[kIPT], ax[kIPT], ay[kIPT];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+        xi2[k] = pk(xi[k], xi[k]);
+        yi2[k] = pk(yi[k], yi[k]);
+        nq2[k] = pk(-qi[k], -qi[k]);
+        ax[k] = pk(0.f, 0.f);
+        ay[k] = pk(0.f, 0.f);
+    }
+    const int quads = jmax >> 2;
+    const ulonglong2* x4 = reinterpret_cast<const ulonglong2*>(sx);
+    const ulonglong2* y4 = reinterpret_cast<const ulonglong2*>(sy);
+    const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(st);
+#pragma unroll 1
+    for (int jq = 0; jq < quads; ++jq) {
+        const ulonglong2 X = x4[jq], Y = y4[jq];            // 4 j per LDS.128
+        ulonglong2 T = make_ulonglong2(0ull, 0ull);
+        if (MODE == 2) T = t4[jq];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            {
-                const float dx = o.x - xi[k], dy = o.y - yi[k];
-                float s;
-                if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
-                else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
-                else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t0, L);
-                fx[k] = fmaf(dx, s, fx[k]);
-                fy[k] = fmaf(dy, s, fy[k]);
-            }
-            {
-                const float dx = o.z - xi[k], dy = o.w - yi[k];
-                float s;
-                if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
-                else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
-                else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t1, L);
-                fx[k] = fmaf(dx, s, fx[k]);
-                fy[k] = fmaf(dy, s, fy[k]);
-            }
+            far_pair2<MODE>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull, c,
+                            ax[k], ay[k]);
+            far_pair2<MODE>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull, c,
+                            ax[k], ay[k]);
         }
     }
-    if (jmax & 1) {
-        const float2 o = sxy[jmax - 1];
-        const float t0 = st[jmax - 1];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+        float a, b;
+        upk(ax[k], a, b); fx[k] += a + b;
+        upk(ay[k], a, b); fy[k] += a + b;
+    }
+    for (int j = quads << 2; j < jmax; ++j) {               // ragged tail of the last tile
+        const float ox = sx[j], oy = sy[j], tj = st[j];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            const float dx = o.x - xi[k], dy = o.y - yi[k];
-            float s;
-            if (MODE == 0) s = pair_far<false, CLAMP>(dx, dy, L);
-            else if (MODE == 1) s = pair_far<true, CLAMP>(dx, dy, L);
-            else s = pair_far_q<CLAMP>(dx, dy, qi[k] * t0, L);
-            fx[k] = fmaf(dx, s, fx[k]);
-            fy[k] = fmaf(dy, s, fy[k]);
+            const float dx = ox - xi[k], dy = oy - yi[k];
+            const float sc = pair_far_impl<MODE, false>(dx, dy, qi[k] * tj, L);
+            fx[k] = fmaf(dx, sc, fx[k]);
+            fy[k] = fmaf(dy, sc, fy[k]);
         }
     }
 }
 
-__device__ __forceinline__ void near_tile(const float2* __restrict__ sxy, const float* __restrict__ st,
-                                          int jmax, const float (&xi)[kIPT], const float (&yi)[kIPT],
+// Scalar far path with the +-12 clamp, only used when the strengths make |net| >= 12 possible
+// beyond d = 9 (never with the reference's defaults).
+template <int MODE>
+__device__ __forceinline__ void far_tile_clamped(const float* __restrict__ sx,
+                                                 const float* __restrict__ sy,
+                                                 const float* __restrict__ st, int jmax,
+                                                 const float (&xi)[kIPT], const float (&yi)[kIPT],
+                                                 const float (&qi)[kIPT], float (&fx)[kIPT],
+                                                 float (&fy)[kIPT], const LawParams& L)
+{
+    for (int j = 0; j < jmax; ++j) {
+        const float ox = sx[j], oy = sy[j], tj = st[j];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            const float dx = ox - xi[k], dy = oy - yi[k];
+            const float sc = pair_far_impl<MODE, true>(dx, dy, qi[k] * tj, L);
+            fx[k] = fmaf(dx, sc, fx[k]);
+            fy[k] = fmaf(dy, sc, fy[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void near_tile(const float* __restrict__ sx, const float* __restrict__ sy,
+                                          const float* __restrict__ st, int jmax,
+                                          const float (&xi)[kIPT], const float (&yi)[kIPT],
                                           const float (&ti)[kIPT], float (&fx)[kIPT],
                                           float (&fy)[kIPT], const LawParams& L)
 {
     for (int j = 0; j < jmax; ++j) {
-        const float2 o = sxy[j];
-        const float tj = st[j];
+        const float ox = sx[j], oy = sy[j], tj = st[j];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            const float dx = o.x - xi[k], dy = o.y - yi[k];
+            const float dx = ox - xi[k], dy = oy - yi[k];
             const float s = pair_general(dx, dy, ti[k], tj, L);
             fx[k] = fmaf(dx, s, fx[k]);
             fy[k] = fmaf(dy, s, fy[k]);
@@ -192,15 +315,20 @@ __device__ __forceinline__ void near_tile(const float2* __restrict__ sxy, const 
     }
 }
 
+// grid = (n_iblocks, n_seg): block (b, s) accumulates the force of j tiles
+// [s * tiles_per_seg, (s+1) * tiles_per_seg) on the 1024 nucleons of i-block b and writes
+// float64 partial sums to partial[s][i - i0].  Splitting the j range keeps >= ~10 work units
+// per resident-block slot whatever N and the number of ranks are (wave quantisation was
+// costing 18 % at N = 1M on one GPU and > 50 % on eight).
 template <bool CLAMP>
 __global__ void __launch_bounds__(kThreads, 2)
-cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_out,
-                   float2* __restrict__ vel, float2* __restrict__ force,
-                   const uint8_t* __restrict__ isp, int64_t n, int64_t i0, int64_t i1,
-                   CloudWorkspace w, LawParams L, float dt, int far_enabled)
+cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict__ isp, int64_t n,
+                   int64_t i0, int64_t i1, CloudWorkspace w, LawParams L, int far_enabled,
+                   int tiles_per_seg)
 {
-    __shared__ __align__(16) float2 sxy[kTile];
-    __shared__ float st[kTile];
+    __shared__ __align__(16) float sx[kTile];
+    __shared__ __align__(16) float sy[kTile];
+    __shared__ __align__(16) float st[kTile];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t wbase = i0 + (int64_t)blockIdx.x * kIBlock + (int64_t)wid * (32 * kIPT);
@@ -239,22 +367,26 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
     alln = __all_sync(0xffffffffu, alln);
 
     const int64_t n_tiles = n_tiles_of(n);
+    const int64_t t_begin = (int64_t)blockIdx.y * tiles_per_seg;
+    int64_t t_end = t_begin + tiles_per_seg;
+    if (t_end > n_tiles) t_end = n_tiles;
     // software pipeline: the next tile's element is fetched into registers while the current
     // tile is being consumed
     float2 nxt = make_float2(0.f, 0.f);
     float nxt_t = 0.f;
     {
-        const int64_t j = threadIdx.x;
+        const int64_t j = t_begin * kTile + threadIdx.x;
         if (j < n) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
     }
-    for (int64_t tile = 0; tile < n_tiles; ++tile) {
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
         __syncthreads();                               // previous tile fully consumed
-        sxy[threadIdx.x] = nxt;
+        sx[threadIdx.x] = nxt.x;
+        sy[threadIdx.x] = nxt.y;
         st[threadIdx.x] = nxt_t;
         __syncthreads();
         {
             const int64_t j = (tile + 1) * kTile + threadIdx.x;
-            if (j < n) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+            if (j < n && tile + 1 < t_end) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
         }
         const int64_t rem = n - tile * kTile;
         const int jmax = rem < kTile ? (int)rem : kTile;
@@ -266,14 +398,19 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
         const float gy = fmaxf(0.f, fmaxf(bb.y - bymax, bymin - bb.w));
         const bool far = far_enabled && (fmaf(gx, gx, gy * gy) > 81.01f);
         if (far) {
-            if (alln || (tf & kTileAllNeutron))
-                far_tile<0, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
-            else if (allp && (tf & kTileAllProton))
-                far_tile<1, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
-            else
-                far_tile<2, CLAMP>(sxy, st, jmax, xi, yi, qi, fx, fy, L);
+            const int mode = (alln || (tf & kTileAllNeutron)) ? 0
+                             : ((allp && (tf & kTileAllProton)) ? 1 : 2);
+            if (CLAMP) {
+                if (mode == 0) far_tile_clamped<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else if (mode == 1) far_tile_clamped<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else far_tile_clamped<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+            } else {
+                if (mode == 0) far_tile_packed<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else if (mode == 1) far_tile_packed<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else far_tile_packed<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+            }
         } else {
-            near_tile(sxy, st, jmax, xi, yi, ti, fx, fy, L);
+            near_tile(sx, sy, st, jmax, xi, yi, ti, fx, fy, L);
         }
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -284,33 +421,39 @@ cloud_force_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_o
         }
     }
 
-    // containment + integrate, nuclear_forces.py:301-323
-    const float cx = (float)w.centre[0], cy = (float)w.centre[1];
-    const float R = 2.4f * cbrtf((float)n);            // :304
+    double2* part = w.partial + (int64_t)blockIdx.y * (i1 - i0);
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
         const int64_t i = wbase + k * 32 + lane;
-        if (i >= i0 && i < i1) {
-            float2 v = vel[i];
-            float x = xi[k], y = yi[k];
-            // containment is part of the reported force
-            const float cdx = cx - x, cdy = cy - y;
-            const float cd = sqrtf(fmaf(cdy, cdy, cdx * cdx));
-            float Ftx = (float)Fx[k], Fty = (float)Fy[k];
-            if (cd > R * 1.5f && cd > 0.01f) {
-                const float cf = 0.03f * (cd - R) / cd;
-                Ftx = fmaf(cf, cdx, Ftx);
-                Fty = fmaf(cf, cdy, Fty);
-            }
-            v.x = fmaf(Ftx, dt, v.x) * kDamp;
-            v.y = fmaf(Fty, dt, v.y) * kDamp;
-            x = fmaf(v.x, dt, x);
-            y = fmaf(v.y, dt, y);
-            pos_out[i] = make_float2(x, y);
-            vel[i] = v;
-            if (force) force[i] = make_float2(Ftx, Fty);
-        }
+        if (i >= i0 && i < i1) part[i - i0] = make_double2(Fx[k], Fy[k]);
     }
+}
+
+// ---- pass 4: reduce the segment partials in a fixed order, containment + integrate ------------------
+// nuclear_forces.py:301-323
+__global__ void __launch_bounds__(256)
+cloud_integrate_kernel(const float2* __restrict__ pos_in, float2* __restrict__ pos_out,
+                       float2* __restrict__ vel, float2* __restrict__ force, int64_t n, int64_t i0,
+                       int64_t i1, CloudWorkspace w, int n_seg, float dt)
+{
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    double sfx = 0.0, sfy = 0.0;
+    for (int s = 0; s < n_seg; ++s) {
+        const double2 p = w.partial[(int64_t)s * (i1 - i0) + (i - i0)];
+        sfx += p.x;
+        sfy += p.y;
+    }
+    const float cx = (float)w.centre[0], cy = (float)w.centre[1];
+    const float R = 2.4f * cbrtf((float)n);            // :304
+    const float2 p = pos_in[i];
+    float2 v = vel[i];
+    float x = p.x, y = p.y;
+    float Fx = (float)sfx, Fy = (float)sfy;
+    contain_and_integrate(x, y, v.x, v.y, Fx, Fy, cx, cy, R, dt);
+    pos_out[i] = make_float2(x, y);
+    vel[i] = v;
+    if (force) force[i] = make_float2(Fx, Fy);         // containment is part of the reported force
 }
 
 // ---- sort keys -----------------------------------------------------------------------------------
@@ -348,7 +491,8 @@ extern "C" int64_t pyqmd_cloud_workspace_bytes(int64_t n)
 {
     if (n < 0) return PYQMD_ERR_INVALID;
     const int64_t nt = n_tiles_of(n);
-    return 32 + nt * (int64_t)(sizeof(float4) + sizeof(double2) + sizeof(int)) + 64;
+    return 32 + nt * (int64_t)(sizeof(float4) + sizeof(double2) + sizeof(int)) + 512 +
+           partial_entries(n) * (int64_t)sizeof(double2);
 }
 
 extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel, float* force,
@@ -370,16 +514,20 @@ extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel,
     cloud_centre<<<1, 256, 0, st>>>(w, nt, n);
     const int64_t blocks = (i1 - i0 + kIBlock - 1) / kIBlock;
     const int far_enabled = strong > 0.f ? 1 : 0;
+    const int n_seg = segments_for(n, i1 - i0);
+    const int tiles_per_seg = (int)((nt + n_seg - 1) / n_seg);
+    PYQMD_REQUIRE((int64_t)n_seg * (i1 - i0) <= partial_entries(n), "workspace too small");
+    const dim3 grid((unsigned)blocks, (unsigned)n_seg);
+    const float2* pin = reinterpret_cast<const float2*>(pos_in);
     if (L.far_needs_clamp)
-        cloud_force_kernel<true><<<(unsigned)blocks, kThreads, 0, st>>>(
-            reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(pos_out),
-            reinterpret_cast<float2*>(vel), reinterpret_cast<float2*>(force), is_proton, n, i0, i1,
-            w, L, dt, far_enabled);
+        cloud_force_kernel<true><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
+                                                            far_enabled, tiles_per_seg);
     else
-        cloud_force_kernel<false><<<(unsigned)blocks, kThreads, 0, st>>>(
-            reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(pos_out),
-            reinterpret_cast<float2*>(vel), reinterpret_cast<float2*>(force), is_proton, n, i0, i1,
-            w, L, dt, far_enabled);
+        cloud_force_kernel<false><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
+                                                             far_enabled, tiles_per_seg);
+    cloud_integrate_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, st>>>(
+        pin, reinterpret_cast<float2*>(pos_out), reinterpret_cast<float2*>(vel),
+        reinterpret_cast<float2*>(force), n, i0, i1, w, n_seg, dt);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }

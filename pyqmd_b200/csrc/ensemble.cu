@@ -19,12 +19,6 @@
 
 namespace pyqmd {
 
-struct EnsembleSmem {
-    float4* sp;   // [T] x, y, isProton, unused
-    float2* sv;   // [T] velocity staging, only used in a step where some nucleus decays
-    int* scnt;    // [G] live nucleon count per nucleus
-};
-
 // Serial transmutation by the leader thread of one nucleus (rare event).
 // Follows handle_decay's physics slice, nuclear_sim.py:213,215,288-294,349,353.
 __device__ void leader_decay(const pyqmd_ensemble& e, const DrawSource& draws, float4* sp,
@@ -115,17 +109,42 @@ __device__ void leader_decay(const pyqmd_ensemble& e, const DrawSource& draws, f
     daughter_half_life(lookup(e.table, zn), u3, e.dt_decay, T, p, used3);
 }
 
-template <int MAXT>
+// Per-warp sums of the nucleon positions of a block (G == 1: the whole block is one nucleus),
+// written next to the positions so that the centre of mass (nuclear_forces.py:242-243) needs no
+// barrier of its own; summed by every thread in warp order, i.e. deterministically.
+__device__ __forceinline__ void publish_warp_sum(float2* wsum, float x, float y, bool active)
+{
+    float sx = active ? x : 0.f, sy = active ? y : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    }
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = make_float2(sx, sy);
+}
+
+// N3 = true: every unordered pair is evaluated once (F_ij = -F_ji holds exactly for this law:
+// it depends on d and on symmetric type predicates only) on a ring schedule -- nucleon i visits
+// partners i+1 .. i+(n-1)/2 (mod n), plus i+n/2 for the lower half when n is even -- and the
+// reaction is accumulated in a per-warp shared-memory row (no atomics, fixed order, so results
+// are reproducible).  Halves the MUFU and FMA work per ordered pair.  N3 = false is the plain
+// ordered-pair loop, kept for blocks of more than 256 threads where the per-warp reaction rows
+// would not fit in shared memory.
+template <int MAXT, bool N3>
 __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, const LawParams L,
                                                          const int n_steps, const int G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x;
+    const int nW = T >> 5;
     float4* sp = reinterpret_cast<float4*>(smem_raw);
     float2* sv = reinterpret_cast<float2*>(sp + T);
-    int* scnt = reinterpret_cast<int*>(sv + T);
+    float2* react = sv + T;                                  // [nW][T], N3 only
+    float2* wsum = react + (N3 ? nW * T : 0);                // [nW]
+    int* scnt = reinterpret_cast<int*>(wsum + nW);
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
     const int cap = e.cap;
     const int g = tid / cap;
     const int li = tid - g * cap;
@@ -151,6 +170,12 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
     }
     sp[tid] = make_float4(x, y, tp, 0.f);
     if (li == 0 && g < G) scnt[g] = cnt;
+    if (N3)
+        for (int w = 0; w < nW; ++w) react[w * T + tid] = make_float2(0.f, 0.f);
+    publish_warp_sum(wsum, x, y, has_nuc && li < cnt);
+    // warps that can hold nucleons of this thread's nucleus
+    const int w_lo = gbase >> 5;
+    const int w_hi = min((gbase + cap - 1) >> 5, nW - 1);
 
     // leader-held nucleus state
     int32_t zn = 0;
@@ -185,40 +210,92 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
                 const float4 me = sp[tid];
                 x = me.x; y = me.y; tp = me.z;
                 R = 2.4f * cbrtf((float)cnt);
+                publish_warp_sum(wsum, x, y, has_nuc && li < cnt);
+                __syncthreads();
             }
         } else {
             __syncthreads();
         }
 
-        // ---- all-pairs force, nuclear_forces.py:248-298 ---------------------------------------
         const bool active = has_nuc && li < cnt;
-        float fx = 0.f, fy = 0.f, sx = 0.f, sy = 0.f;
+        float fx = 0.f, fy = 0.f;
+        float cx = 0.f, cy = 0.f;
         if (active) {
+            // ---- centre of mass, nuclear_forces.py:242-243 ----------------------------------------
             const float4* tile = sp + gbase;
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const float4 o = tile[j];
-                const float dx = o.x - x, dy = o.y - y;
-                const float sc = pair_general(dx, dy, tp, o.z, L);
-                fx = fmaf(dx, sc, fx);
-                fy = fmaf(dy, sc, fy);
-                sx += o.x;                                  // centre of mass, :242-243
-                sy += o.y;
-            }
-            const float inv_n = 1.0f / (float)cnt;
-            float cx = sx * inv_n, cy = sy * inv_n;
             if (e.centre) {                                 // caller-supplied `center`, :64
                 cx = e.centre[2 * (int64_t)nuc];
                 cy = e.centre[2 * (int64_t)nuc + 1];
+            } else {
+                float sx = 0.f, sy = 0.f;
+                if (G == 1) {
+                    for (int w = 0; w < nW; ++w) { sx += wsum[w].x; sy += wsum[w].y; }
+                } else {
+                    for (int j = 0; j < cnt; ++j) { sx += tile[j].x; sy += tile[j].y; }
+                }
+                const float inv_n = 1.0f / (float)cnt;
+                cx = sx * inv_n;
+                cy = sy * inv_n;
+            }
+            // ---- all-pairs force, nuclear_forces.py:248-298 ---------------------------------------
+            if (N3) {
+                float2* row = react + warp * T + gbase;
+                const int half = (cnt - 1) >> 1;
+                int j = li;
+#pragma unroll 2
+                for (int k = 0; k < half; ++k) {
+                    j = (j + 1 == cnt) ? 0 : j + 1;         // partner (li + k + 1) mod cnt
+                    const float4 o = tile[j];
+                    const float dx = o.x - x, dy = o.y - y;
+                    const float sc = pair_general(dx, dy, tp, o.z, L);
+                    const float px = dx * sc, py = dy * sc;
+                    fx += px;
+                    fy += py;
+                    float2 r = row[j];                      // reaction on the partner
+                    r.x -= px;
+                    r.y -= py;
+                    row[j] = r;
+                }
+                if (!(cnt & 1) && li < (cnt >> 1)) {        // antipodal partner, even n
+                    j = li + (cnt >> 1);
+                    const float4 o = tile[j];
+                    const float dx = o.x - x, dy = o.y - y;
+                    const float sc = pair_general(dx, dy, tp, o.z, L);
+                    const float px = dx * sc, py = dy * sc;
+                    fx += px;
+                    fy += py;
+                    float2 r = row[j];
+                    r.x -= px;
+                    r.y -= py;
+                    row[j] = r;
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 o = tile[j];
+                    const float dx = o.x - x, dy = o.y - y;
+                    const float sc = pair_general(dx, dy, tp, o.z, L);
+                    fx = fmaf(dx, sc, fx);
+                    fy = fmaf(dy, sc, fy);
+                }
+            }
+        }
+        __syncthreads();                 // Jacobi: all reads (and all reactions) before any write
+        if (active) {
+            if (N3) {
+                for (int w = w_lo; w <= w_hi; ++w) {        // fixed order: reproducible
+                    const float2 r = react[w * T + tid];
+                    react[w * T + tid] = make_float2(0.f, 0.f);
+                    fx += r.x;
+                    fy += r.y;
+                }
             }
             contain_and_integrate(x, y, vel.x, vel.y, fx, fy, cx, cy, R, e.dt_phys);   // :301-323
-        }
-        __syncthreads();                                    // Jacobi: all reads before any write
-        if (active) {
             sp[tid] = make_float4(x, y, tp, 0.f);
             if (e.force && s == n_steps - 1)
                 reinterpret_cast<float2*>(e.force)[off + li] = make_float2(fx, fy);
         }
+        if (G == 1) publish_warp_sum(wsum, x, y, active);
     }
 
     if (has_nuc && li < cnt) {
@@ -274,13 +351,17 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
     const int T = pick_block_threads(e->cap, &G);
     const int64_t grid = (n_list + G - 1) / G;
     PYQMD_REQUIRE(grid <= 2147483647LL, "too many nuclei for one launch");
-    const size_t smem = (size_t)T * (sizeof(float4) + sizeof(float2)) + (size_t)G * sizeof(int);
+    const int nW = T / 32;
+    const bool n3 = T <= 256;
+    const size_t smem = (size_t)T * (sizeof(float4) + sizeof(float2)) +
+                        (n3 ? (size_t)nW * T * sizeof(float2) : 0) + (size_t)nW * sizeof(float2) +
+                        (size_t)G * sizeof(int);
     const LawParams L = make_law_params(e->strong, e->coulomb, e->pauli);
     cudaStream_t st = (cudaStream_t)stream;
-    if (T <= 256)
-        ensemble_kernel<256><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
+    if (n3)
+        ensemble_kernel<256, true><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
     else
-        ensemble_kernel<1024><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
+        ensemble_kernel<1024, false><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }
