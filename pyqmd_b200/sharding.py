@@ -1,0 +1,55 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed).
+
+The reference (OtsoBear/PyQMD) is single-device; this is new work:
+
+* ensembles / decay populations shard by nucleus -- contiguous blocks, global nucleus ids key
+  the RNG, no data-path collective; only counters are summed at reporting time;
+* one big nucleon cloud shards by i-block: every rank holds a full replica of the positions,
+  advances its own block [rank*chunk, (rank+1)*chunk) and the new positions are all-gathered
+  once per step (8 B per nucleon).
+
+These helpers are device-agnostic (they run on CPU tensors over gloo in the CPU test-suite and
+on CUDA tensors over NCCL/NVLink in production).
+"""
+from __future__ import annotations
+
+import torch
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block of units owned by ``rank``: [lo, hi)."""
+    chunk = (n + world - 1) // world
+    lo = min(rank * chunk, n)
+    return lo, min(lo + chunk, n)
+
+
+def cloud_chunk(n: int, world: int) -> int:
+    """Nucleons per rank; replicas are padded to chunk * world rows so the all-gather is regular."""
+    return (n + world - 1) // world
+
+
+def allgather_positions(replica: torch.Tensor, rank: int, world: int, chunk: int, group=None):
+    """In-place all-gather of the rows each rank owns in its [chunk * world, 2] replica."""
+    if world == 1:
+        return replica
+    import torch.distributed as dist
+    mine = replica[rank * chunk:(rank + 1) * chunk]
+    dist.all_gather_into_tensor(replica, mine, group=group)
+    return replica
+
+
+def sum_counters(t: torch.Tensor, group=None):
+    """Sum of per-rank statistics (decays by mode, survivors ...) at reporting time."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def max_over_ranks(seconds: float, device, group=None) -> float:
+    """Device-timed duration as the max over ranks (never wall clock)."""
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

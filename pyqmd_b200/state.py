@@ -75,11 +75,7 @@ def initial_half_lives(zn: np.ndarray, dt_decay: float, rng: np.random.Generator
     return T, p
 
 
-def shard_range(n: int, rank: int, world: int):
-    """Contiguous block of units owned by ``rank`` (nuclei for ensembles / populations)."""
-    chunk = (n + world - 1) // world
-    lo = min(rank * chunk, n)
-    return lo, min(lo + chunk, n)
+from .sharding import allgather_positions, cloud_chunk, shard_range  # noqa: E402,F401
 
 
 # =================================================================================================
@@ -321,9 +317,8 @@ class NucleonCloud:
         self.n = int(pos.shape[0])
         self.dt, self.strengths = float(dt), tuple(float(s) for s in strengths)
         self.rank, self.world, self.group = int(rank), int(world), group
-        self.chunk = (self.n + self.world - 1) // self.world
-        self.i0 = min(self.rank * self.chunk, self.n)
-        self.i1 = min(self.i0 + self.chunk, self.n)
+        self.chunk = cloud_chunk(self.n, self.world)
+        self.i0, self.i1 = shard_range(self.n, self.rank, self.world)
         self.perm = None
         if sort and self.n > 0:
             self.perm = self._sort_perm(pos, isp)
@@ -356,10 +351,7 @@ class NucleonCloud:
                 self.pos.data_ptr(), self.pos_next.data_ptr(), self.vel.data_ptr(),
                 _lib.ptr(self.force), self.is_proton.data_ptr(), self.n, self.i0, self.i1, S, Cc,
                 P, self.dt, self.workspace.data_ptr(), _lib.current_stream()), "pyqmd_cloud_step")
-            if self.world > 1:
-                import torch.distributed as dist
-                mine = self.pos_next[self.rank * self.chunk:(self.rank + 1) * self.chunk]
-                dist.all_gather_into_tensor(self.pos_next, mine, group=self.group)
+            allgather_positions(self.pos_next, self.rank, self.world, self.chunk, self.group)
             self.pos, self.pos_next = self.pos_next, self.pos
             self.steps_done += 1
 

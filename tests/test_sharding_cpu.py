@@ -1,0 +1,94 @@
+"""The N > 1 path on CPU: two processes over gloo exercise the partitioning, the per-step
+position exchange of the i-block-sharded cloud and the counter reduction (no GPU needed)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pyqmd_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = sharding.cloud_chunk(n, world)
+        lo, hi = sharding.shard_range(n, rank, world)
+        # every rank starts from the same replica; each advances only its own i-block
+        g = torch.Generator().manual_seed(5)
+        replica = torch.zeros(chunk * world, 2)
+        replica[:n] = torch.rand(n, 2, generator=g)
+        nxt = torch.full_like(replica, -1.0)
+        for step in range(3):
+            nxt[lo:hi] = replica[lo:hi] * 2.0 + (step + 1)           # "integrate" own block
+            sharding.allgather_positions(nxt, rank, world, chunk)
+            replica, nxt = nxt, replica
+        # single-process reference of the same 3 steps
+        g = torch.Generator().manual_seed(5)
+        ref = torch.rand(n, 2, generator=g)
+        for step in range(3):
+            ref = ref * 2.0 + (step + 1)
+        ok = torch.equal(replica[:n], ref)
+        # counters: decays per mode summed over ranks; device time = max over ranks
+        c = torch.tensor([rank + 1, 10 * (rank + 1)], dtype=torch.int64)
+        sharding.sum_counters(c)
+        t = sharding.max_over_ranks(0.5 + rank, "cpu")
+        out.put((rank, bool(ok), c.tolist(), t, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 11, 4097])
+def test_cloud_exchange_world2(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    spans = []
+    for rank, ok, c, t, span in res:
+        assert ok, f"rank {rank}: replica differs from the single-process result"
+        assert c == [3, 30] and t == 1.5
+        spans.append(span)
+    assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == n
+
+
+def test_shard_ranges_partition_everything():
+    for n in (0, 1, 7, 8, 1000, 65536, 1_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert sharding.cloud_chunk(n, w) * w >= n
+
+
+def test_global_ids_make_sharding_invisible_to_the_rng():
+    """Philox counters use the global nucleus id, so a nucleus draws the same uniforms whichever
+    rank owns it (checked with the oracle's Philox; the GPU suite checks the kernels)."""
+    from oracle import oracle as orc
+    n, world = 1000, 4
+    whole = orc.philox_uniforms(99, 0, n, 3, 0)
+    parts = []
+    for r in range(world):
+        lo, hi = sharding.shard_range(n, r, world)
+        parts.append(orc.philox_uniforms(99, lo, hi - lo, 3, 0))
+    assert np.array_equal(np.concatenate(parts), whole)
