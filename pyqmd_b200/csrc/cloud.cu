@@ -151,29 +151,6 @@ __global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_
 // pairs, so the 14 FMA-pipe operations of a far pair cost 7 issue slots instead of 14 and the
 // kernel moves from issue-bound (ncu r01a: 82 % issue, 18 instr/pair) towards the MUFU limit of
 // 2 special-function ops per pair.
-typedef unsigned long long f32x2;
-
-__device__ __forceinline__ f32x2 pk(float lo, float hi)
-{
-    f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
-{
-    f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-
 struct FarConsts {
     f32x2 kexp, logA, c3, c2, c1, one, e2, ne, negC;
 };

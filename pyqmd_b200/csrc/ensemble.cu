@@ -313,6 +313,323 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// ensemble_pair_kernel: the production kernel for nuclei of up to 512 nucleons.
+//
+// Each thread owns TWO nucleons (2t, 2t+1) of its nucleus, so every evaluation of the law is a
+// packed f32x2 evaluation of (i_a, j) and (i_b, j): all FMA-pipe arithmetic issues as
+// FADD2/FMUL2/FFMA2 (half the issue slots), compares/selects/MUFU stay per element.  Newton's
+// third law is used on a ring of "super-particles" (= the nucleon pairs of the threads): thread t
+// visits super-partners t+1 .. t+(m-1)/2 (mod m) -- plus the antipode for the lower half when m is
+// even -- and its own pair (2t, 2t+1) once; the reaction on partner j (summed over i_a, i_b) goes
+// to a per-warp shared-memory row (no atomics; fixed order => bit-reproducible).
+//
+// Shared memory, per block of G nuclei x capT threads (capS = 2 capT slots per nucleus):
+//   A4   float4[2 * G * capS]  (x, x, y, y) per slot, canonical [0, M) then mirror [M, 2M) so the
+//                              ring never wraps (M = cnt rounded up to even)
+//   T2   float2[2 * G * capS]  (isProton, isProton), same indexing
+//   spc  float4[G * capS], sv float2[G * capS]   canonical staging used only when a nucleus decays
+//   react float2[nW][G * capS] per-warp reaction rows
+//   wsum float4[nW]            per-warp position sums (first / second nucleus present in the warp)
+// An odd nucleon count is padded with a ghost neutron parked at (1e5, 1e5): every term of the law
+// is exactly 0 at that distance, so it needs no masking in the pair loop.
+constexpr float kGhost = 1.0e5f;
+
+struct PairSmem {
+    float4* A4;
+    float2* T2;
+    float4* spc;
+    float2* sv;
+    float2* react;
+    float4* wsum;
+    int* scnt;
+};
+
+// Slots are stored split by parity (even slots of a nucleus first, then the odd ones) so that the
+// lanes of a warp, which visit slots 2(t+k) resp. 2(t+k)+1, touch consecutive 16-byte words: no
+// shared-memory bank conflicts (ncu r01c showed 2-way conflicts with the interleaved layout).
+// Within each parity half, super-index u = s >> 1 runs over [0, m) and is mirrored at [m, 2m).
+__device__ __forceinline__ void put_slot(const PairSmem& S, int gb2, int capS, int m, int s, float x,
+                                         float y, float tp)
+{
+    const float4 a = make_float4(x, x, y, y);
+    const float2 t = make_float2(tp, tp);
+    const int idx = gb2 + (s & 1) * capS + (s >> 1);
+    S.A4[idx] = a;
+    S.A4[idx + m] = a;
+    S.T2[idx] = t;
+    S.T2[idx + m] = t;
+}
+
+// per-warp position sums, split by nucleus (a warp spans at most two nuclei when capT >= 32)
+__device__ __forceinline__ void publish_pair_sums(float4* wsum, int capT, int g, float vx, float vy)
+{
+    const int gfirst = ((threadIdx.x & ~31)) / capT;
+    const bool first = (g == gfirst);
+    float a = first ? vx : 0.f, b = first ? vy : 0.f;
+    float c = first ? 0.f : vx, d = first ? 0.f : vy;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = make_float4(a, b, c, d);
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 3) ensemble_pair_kernel(const pyqmd_ensemble e,
+                                                              const LawParams L, const int n_steps,
+                                                              const int G, const int capT)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int nW = T >> 5;
+    const int capS = 2 * capT;
+    const int nSlots = G * capS;
+    PairSmem S;
+    S.A4 = reinterpret_cast<float4*>(smem_raw);
+    S.spc = S.A4 + 2 * nSlots;
+    S.wsum = S.spc + nSlots;
+    S.T2 = reinterpret_cast<float2*>(S.wsum + nW);
+    S.sv = S.T2 + 2 * nSlots;
+    S.react = S.sv + nSlots;
+    S.scnt = reinterpret_cast<int*>(S.react + nW * nSlots);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int g = tid / capT;
+    const int t = tid - g * capT;
+    const int gb = g * capS;             // canonical slot base (spc, sv, react)
+    const int gb2 = 2 * gb;              // base in the mirrored arrays
+    const int s0 = 2 * t, s1 = 2 * t + 1;
+    const int64_t q = (int64_t)blockIdx.x * G + g;
+    const bool has_nuc = (g < G) && (q < e.n_list);
+    const int nuc = has_nuc ? (e.list ? e.list[q] : (int)q) : -1;
+    const bool leader = has_nuc && t == 0;
+
+    int cnt = 0;
+    int64_t off = 0;
+    if (has_nuc) {
+        cnt = e.count[nuc];
+        off = e.offset[nuc];
+    }
+    int m = (cnt + 1) >> 1, M = 2 * m;
+    bool active = has_nuc && t < m;
+    bool real1 = active && s1 < cnt;
+    float x0 = kGhost, y0 = kGhost, t0 = 0.f, x1 = kGhost, y1 = kGhost, t1 = 0.f;
+    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    if (active) {
+        const float2 p = reinterpret_cast<const float2*>(e.pos)[off + s0];
+        v0 = reinterpret_cast<const float2*>(e.vel)[off + s0];
+        x0 = p.x; y0 = p.y;
+        t0 = e.is_proton[off + s0] ? 1.0f : 0.0f;
+    }
+    if (real1) {
+        const float2 p = reinterpret_cast<const float2*>(e.pos)[off + s1];
+        v1 = reinterpret_cast<const float2*>(e.vel)[off + s1];
+        x1 = p.x; y1 = p.y;
+        t1 = e.is_proton[off + s1] ? 1.0f : 0.0f;
+    }
+    if (active) {
+        put_slot(S, gb2, capS, m, s0, x0, y0, t0);
+        put_slot(S, gb2, capS, m, s1, x1, y1, t1);
+    }
+    if (t == 0 && g < G) S.scnt[g] = cnt;
+    for (int k = tid; k < nW * nSlots; k += T) S.react[k] = make_float2(0.f, 0.f);
+    publish_pair_sums(S.wsum, capT, g, (active ? x0 : 0.f) + (real1 ? x1 : 0.f),
+                      (active ? y0 : 0.f) + (real1 ? y1 : 0.f));
+    const int w_lo = (g * capT) >> 5;
+    const int w_hi = min((g * capT + capT - 1) >> 5, nW - 1);
+
+    int32_t zn = 0;
+    double T_half = 0.0, p_dec = -1.0;
+    if (leader && e.decay_enabled) {
+        zn = e.zn[nuc];
+        T_half = e.half_life[nuc];
+        p_dec = e.p_decay[nuc];
+    }
+    const DrawSource draws{e.uniforms, e.seed, e.uniforms_n};
+    const GenConsts gc = make_gen_consts(L);
+    float R = 2.4f * cbrtf((float)cnt);                     // nuclear_forces.py:304
+
+    for (int s = 0; s < n_steps; ++s) {
+        // ---- decay test: Nucleus.should_decay, particles.py:126-147 --------------------------
+        if (e.decay_enabled) {
+            bool fire = false;
+            const uint32_t step_abs = e.step0 + (uint32_t)s;
+            if (leader && p_dec >= 0.0) {                   // stable: no draw (:129-130)
+                const double u0 = draws.one((uint64_t)(e.id_base + nuc), nuc, step_abs, s, 0);
+                fire = u0 < p_dec;                          // :147
+            }
+            if (__syncthreads_or(fire)) {
+                if (active) {
+                    S.spc[gb + s0] = make_float4(x0, y0, t0, 0.f);
+                    S.sv[gb + s0] = v0;
+                }
+                if (real1) {
+                    S.spc[gb + s1] = make_float4(x1, y1, t1, 0.f);
+                    S.sv[gb + s1] = v1;
+                }
+                __syncthreads();
+                if (fire) {
+                    leader_decay(e, draws, S.spc, S.sv, gb, cnt, nuc, step_abs, s, zn, T_half, p_dec);
+                    S.scnt[g] = cnt;
+                }
+                __syncthreads();
+                if (g < G) cnt = S.scnt[g];
+                m = (cnt + 1) >> 1;
+                M = 2 * m;
+                active = has_nuc && t < m;
+                real1 = active && s1 < cnt;
+                x0 = y0 = x1 = y1 = kGhost;
+                t0 = t1 = 0.f;
+                v0 = v1 = make_float2(0.f, 0.f);
+                if (active) {
+                    const float4 a = S.spc[gb + s0];
+                    x0 = a.x; y0 = a.y; t0 = a.z;
+                    v0 = S.sv[gb + s0];
+                }
+                if (real1) {
+                    const float4 a = S.spc[gb + s1];
+                    x1 = a.x; y1 = a.y; t1 = a.z;
+                    v1 = S.sv[gb + s1];
+                }
+                __syncthreads();                            // staging consumed before slots move
+                if (active) {
+                    put_slot(S, gb2, capS, m, s0, x0, y0, t0);
+                    put_slot(S, gb2, capS, m, s1, x1, y1, t1);
+                }
+                R = 2.4f * cbrtf((float)cnt);
+                publish_pair_sums(S.wsum, capT, g, (active ? x0 : 0.f) + (real1 ? x1 : 0.f),
+                                  (active ? y0 : 0.f) + (real1 ? y1 : 0.f));
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+
+        float f0x = 0.f, f0y = 0.f, f1x = 0.f, f1y = 0.f;
+        float cx = 0.f, cy = 0.f;
+        if (active) {
+            // ---- centre of mass, nuclear_forces.py:242-243 ----------------------------------------
+            if (e.centre) {                                 // caller-supplied `center`, :64
+                cx = e.centre[2 * (int64_t)nuc];
+                cy = e.centre[2 * (int64_t)nuc + 1];
+            } else {
+                float sx = 0.f, sy = 0.f;
+                if (capT >= 32) {
+                    for (int w = w_lo; w <= w_hi; ++w) {
+                        const float4 ws = S.wsum[w];
+                        const int gf = (w << 5) / capT;
+                        if (gf == g) { sx += ws.x; sy += ws.y; }
+                        else if (gf + 1 == g) { sx += ws.z; sy += ws.w; }
+                    }
+                } else {
+                    for (int j = 0; j < cnt; ++j) {
+                        const float4 a = S.A4[gb2 + (j & 1) * capS + (j >> 1)];
+                        sx += a.x;
+                        sy += a.z;
+                    }
+                }
+                const float inv_n = 1.0f / (float)cnt;
+                cx = sx * inv_n;
+                cy = sy * inv_n;
+            }
+            // ---- all-pairs force, nuclear_forces.py:248-298 ---------------------------------------
+            const ulonglong2* Ag = reinterpret_cast<const ulonglong2*>(S.A4 + gb2);
+            const float2* Tg = S.T2 + gb2;
+            float2* row = S.react + warp * nSlots + gb;
+            const f32x2 xi2 = pk(x0, x1), yi2 = pk(y0, y1);
+            const f32x2 nq2 = pk(-L.C * t0, -L.C * t1);
+            f32x2 fx2 = pk(0.f, 0.f), fy2 = pk(0.f, 0.f);
+            const int capT_ = capT;
+            auto visit = [&](int u, int par) {              // partner slot 2u + par
+                const ulonglong2 o = Ag[par * capS + u];
+                const float2 tt = Tg[par * capS + u];
+                const f32x2 dx2 = sub2(o.x, xi2), dy2 = sub2(o.y, yi2);
+                const f32x2 sc2 = pair_general2(dx2, dy2, t0, t1, tt.x, pk(tt.x, tt.y), nq2, gc, L);
+                const f32x2 px2 = mul2(dx2, sc2), py2 = mul2(dy2, sc2);
+                fx2 = add2(fx2, px2);
+                fy2 = add2(fy2, py2);
+                float pa, pb, qa, qb;
+                upk(px2, pa, pb);
+                upk(py2, qa, qb);
+                const int ur = (u >= m) ? u - m : u;
+                float2 r = row[par * capT_ + ur];            // reaction on the partner
+                r.x -= pa + pb;
+                r.y -= qa + qb;
+                row[par * capT_ + ur] = r;
+            };
+            const int hs = (m - 1) >> 1;
+            for (int k = 1; k <= hs; ++k) {
+                visit(t + k, 0);
+                visit(t + k, 1);
+            }
+            if (!(m & 1) && t < (m >> 1)) {                 // antipodal super-partner, even m
+                visit(t + (m >> 1), 0);
+                visit(t + (m >> 1), 1);
+            }
+            upk(fx2, f0x, f1x);
+            upk(fy2, f0y, f1y);
+            {                                               // the thread's own pair (2t, 2t+1)
+                const float dx = x1 - x0, dy = y1 - y0;
+                const float sc = pair_general(dx, dy, t0, t1, L);
+                f0x = fmaf(dx, sc, f0x);  f0y = fmaf(dy, sc, f0y);
+                f1x = fmaf(-dx, sc, f1x); f1y = fmaf(-dy, sc, f1y);
+            }
+        }
+        __syncthreads();                 // Jacobi: all reads (and all reactions) before any write
+        if (active) {
+            for (int w = w_lo; w <= w_hi; ++w) {            // fixed order: reproducible
+                float2* rw = S.react + w * nSlots + gb;
+                const float2 ra = rw[t], rb = rw[capT + t];   // slots 2t (even half), 2t+1 (odd half)
+                rw[t] = make_float2(0.f, 0.f);
+                rw[capT + t] = make_float2(0.f, 0.f);
+                f0x += ra.x; f0y += ra.y;
+                f1x += rb.x; f1y += rb.y;
+            }
+            contain_and_integrate(x0, y0, v0.x, v0.y, f0x, f0y, cx, cy, R, e.dt_phys);   // :301-323
+            if (real1) contain_and_integrate(x1, y1, v1.x, v1.y, f1x, f1y, cx, cy, R, e.dt_phys);
+            put_slot(S, gb2, capS, m, s0, x0, y0, t0);
+            if (real1) put_slot(S, gb2, capS, m, s1, x1, y1, t1);
+            if (e.force && s == n_steps - 1) {
+                reinterpret_cast<float2*>(e.force)[off + s0] = make_float2(f0x, f0y);
+                if (real1) reinterpret_cast<float2*>(e.force)[off + s1] = make_float2(f1x, f1y);
+            }
+        }
+        publish_pair_sums(S.wsum, capT, g, (active ? x0 : 0.f) + (real1 ? x1 : 0.f),
+                          (active ? y0 : 0.f) + (real1 ? y1 : 0.f));
+    }
+
+    if (active) {
+        reinterpret_cast<float2*>(e.pos)[off + s0] = make_float2(x0, y0);
+        reinterpret_cast<float2*>(e.vel)[off + s0] = v0;
+        e.is_proton[off + s0] = (t0 != 0.f) ? 1 : 0;
+    }
+    if (real1) {
+        reinterpret_cast<float2*>(e.pos)[off + s1] = make_float2(x1, y1);
+        reinterpret_cast<float2*>(e.vel)[off + s1] = v1;
+        e.is_proton[off + s1] = (t1 != 0.f) ? 1 : 0;
+    }
+    if (leader) {
+        e.count[nuc] = cnt;
+        if (e.decay_enabled) {
+            e.zn[nuc] = zn;
+            e.half_life[nuc] = T_half;
+            e.p_decay[nuc] = p_dec;
+        }
+    }
+}
+
+static size_t pair_smem_bytes(int T, int G, int capT)
+{
+    const size_t nW = T / 32, nSlots = (size_t)G * 2 * capT;
+    return sizeof(float4) * (2 * nSlots + nSlots + nW) +
+           sizeof(float2) * (2 * nSlots + nSlots + nW * nSlots) + sizeof(int) * G + 16;
+}
+
 static int pick_block_threads(int cap, int* G_out)
 {
     if (cap > 128) {
@@ -351,6 +668,43 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
     const int T = pick_block_threads(e->cap, &G);
     const int64_t grid = (n_list + G - 1) / G;
     PYQMD_REQUIRE(grid <= 2147483647LL, "too many nuclei for one launch");
+    // production path: two nucleons per thread, packed f32x2, Newton-3 ring
+    if (e->cap <= 512) {
+        const int capT = (e->cap + 1) / 2;
+        int Gp = 1;
+        const int Tp = pick_block_threads(capT, &Gp);
+        const size_t sm = pair_smem_bytes(Tp, Gp, capT);
+        if (sm <= 200 * 1024) {
+            const int64_t gridp = (n_list + Gp - 1) / Gp;
+            PYQMD_REQUIRE(gridp <= 2147483647LL, "too many nuclei for one launch");
+            const LawParams Lp = make_law_params(e->strong, e->coulomb, e->pauli);
+            static bool attr_set = false;
+            if (!attr_set) {
+                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<224>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      200 * 1024));
+                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<224>,
+                                                      cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                      cudaSharedmemCarveoutMaxShared));
+                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<256>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      200 * 1024));
+                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<256>,
+                                                      cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                      cudaSharedmemCarveoutMaxShared));
+                attr_set = true;
+            }
+            // blocks of <= 224 threads get 96 registers per thread at 3 blocks / SM
+            if (Tp <= 224)
+                ensemble_pair_kernel<224><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
+                    d, Lp, n_steps, Gp, capT);
+            else
+                ensemble_pair_kernel<256><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
+                    d, Lp, n_steps, Gp, capT);
+            PYQMD_CUDA_CHECK(cudaGetLastError());
+            return PYQMD_OK;
+        }
+    }
     const int nW = T / 32;
     const bool n3 = T <= 256;
     const size_t smem = (size_t)T * (sizeof(float4) + sizeof(float2)) +

@@ -63,6 +63,38 @@ __device__ __forceinline__ float mufu_sqrt(float x)
     float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
 
+// ---- packed FP32 (Blackwell add/sub/mul/fma.f32x2 -> FADD2/FMUL2/FFMA2) -----------------------------
+// One instruction works on two pairs: FMA-pipe work costs half the issue slots, which is what
+// both hot kernels were limited by (ncu r01a: 82 % issue utilisation).
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi)
+{
+    f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ f32x2 pk1(float v) { return pk(v, v); }
+
 // General pair: every branch of the law, evaluated with selects (no divergence).
 //   dx,dy  = r_j - r_i                                  [253-254]
 //   ti,tj  = 1.0f for a proton, 0.0f for a neutron
@@ -72,7 +104,9 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
                                               const LawParams& L)
 {
     const float d2 = fmaf(dy, dy, dx * dx);                       // [255]
-    const float rinv = mufu_rsqrt(fmaxf(d2, 1e-12f));
+    // d2 == 0 (self pair / coincident nucleons) gives inf/NaN below; the final select on
+    // d2 < 0.01 discards them (FSEL does not propagate the unselected NaN)
+    const float rinv = mufu_rsqrt(d2);
     const float d = d2 * rinv;                                    // [260]
 
     // hard core: -60 * ((4.25-d)/4.25)^1.5 for d < 4.25           [264-267]
@@ -104,6 +138,78 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
     net = fminf(fmaxf(net, -kMaxForce), kMaxForce);               // [294]
     const float s = net * rinv;                                   // [297-298]: (dx*net)/d
     return (d2 < kSkipD2) ? 0.0f : s;                             // [257]
+}
+
+// Two general pairs at once: nucleons (i_a, i_b) of one thread against the same partner j, all
+// FMA-pipe arithmetic packed (f32x2), compares / selects / min-max / MUFU per element.
+//   dx, dy = (r_j - r_ia, r_j - r_ib);  tj2 = (t_j, t_j);  nq = (-C t_ia, -C t_ib).
+// Same arithmetic as pair_general.
+struct GenConsts {
+    f32x2 nInvHard, one, eps, negCoreK, n60, negP, kPauli;
+};
+
+__device__ __forceinline__ GenConsts make_gen_consts(const LawParams& L)
+{
+    GenConsts c;
+    c.nInvHard = pk1(-1.0f / kHardD);
+    c.one = pk1(1.0f);
+    c.eps = pk1(kEps);
+    c.negCoreK = pk1(-L.coreK);
+    c.n60 = pk1(-60.0f);
+    c.negP = pk1(-L.P);
+    c.kPauli = pk1(-2.0f * kLog2e / kPauliD);
+    return c;
+}
+
+__device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, float tb, float tj,
+                                               f32x2 tj2, f32x2 nq, const GenConsts& c,
+                                               const LawParams& L)
+{
+    const f32x2 d2 = fma2(dy, dy, mul2(dx, dx));                    // [255]
+    float d2a, d2b;
+    upk(d2, d2a, d2b);
+    const f32x2 rinv = pk(mufu_rsqrt(d2a), mufu_rsqrt(d2b));
+    const f32x2 d = mul2(d2, rinv);                                 // [260]
+    // hard core                                                     [264-267]
+    float ova, ovb;
+    upk(fma2(d, c.nInvHard, c.one), ova, ovb);
+    ova = fmaxf(ova, 0.f);
+    ovb = fmaxf(ovb, 0.f);
+    const f32x2 hc = mul2(pk(ova, ovb), pk(mufu_sqrt(ova), mufu_sqrt(ovb)));
+    // strong                                                        [273-281]
+    const f32x2 a = add2(d, c.eps), b = add2(d2, c.eps);
+    float aba, abb;
+    upk(mul2(a, b), aba, abb);
+    const f32x2 rab = pk(mufu_rcp(aba), mufu_rcp(abb));
+    const f32x2 inv_a = mul2(rab, b), inv_b = mul2(rab, a);
+    const bool attr_a = d2a < kAttrD * kAttrD, attr_b = d2b < kAttrD * kAttrD;
+    const f32x2 kexp = pk(attr_a ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f),
+                          attr_b ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f));
+    const f32x2 coef = pk(attr_a ? L.attrK : L.tailK, attr_b ? L.attrK : L.tailK);
+    float ea, eb;
+    upk(mul2(d, kexp), ea, eb);
+    const f32x2 e = pk(mufu_ex2(ea), mufu_ex2(eb));
+    float sfa, sfb, sca, scb;
+    upk(mul2(mul2(coef, e), inv_a), sfa, sfb);
+    upk(mul2(c.negCoreK, inv_b), sca, scb);
+    const f32x2 strong = pk(d2a < kCoreD * kCoreD ? sca : sfa, d2b < kCoreD * kCoreD ? scb : sfb);
+    f32x2 net = fma2(hc, c.n60, strong);
+    // Coulomb                                                       [284-285]
+    net = fma2(mul2(nq, tj2), inv_b, net);
+    // Pauli                                                         [288-291]
+    float pa, pb;
+    upk(mul2(d, c.kPauli), pa, pb);
+    const f32x2 netp = fma2(c.negP, pk(mufu_ex2(pa), mufu_ex2(pb)), net);
+    float na, nb, npa, npb;
+    upk(net, na, nb);
+    upk(netp, npa, npb);
+    na = (ta == tj && d2a < kPauliD * kPauliD) ? npa : na;
+    nb = (tb == tj && d2b < kPauliD * kPauliD) ? npb : nb;
+    na = fminf(fmaxf(na, -kMaxForce), kMaxForce);                   // [294]
+    nb = fminf(fmaxf(nb, -kMaxForce), kMaxForce);
+    float sa, sb;
+    upk(mul2(pk(na, nb), rinv), sa, sb);                            // [297-298]
+    return pk(d2a < kSkipD2 ? 0.f : sa, d2b < kSkipD2 ? 0.f : sb);  // [257]
 }
 
 // Far pair, valid only when the caller has proved d >= 9 for the pair (tile bounding boxes):
