@@ -108,6 +108,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[kernel]["bytes"]
+    except Exception:
+        return None
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -197,7 +206,8 @@ def run_reference(args):
         value = float(np.mean([v for v, _ in vals]))
         ms = float(np.mean([d for _, d in vals])) * 1e3
         sample = f"{n_i} i-nucleons x 65,535 partners of a 65,536-nucleon PCG64(1234) cloud per step"
-        cfg = {"workload": f"C4 single nucleon cloud N={args.cloud_n} (sampled)"}
+        cfg = {"workload": f"C4 single 2-D nucleon cloud N={args.cloud_n} (40% protons), all-pairs, "
+                           f"i-block sharded x{args.gpus}"}
         extra = {}
     else:
         isotopes = README_ISOTOPES if args.workload == "mixed" else (PB208,)
@@ -210,9 +220,10 @@ def run_reference(args):
         value = float(np.mean([v for v, _, _ in vals]))
         ms = float(np.mean([d for _, _, d in vals])) * 1e3
         sample = f"{n_nuc} reference-layout nuclei x 1 sub-step per step"
-        cfg = {"workload": ("C3 mixed ensemble, nine preset isotopes" if args.workload == "mixed"
-                            else "C2 ensemble of 65,536 independent Pb-208 nuclei per GPU") +
-                           " (bounded sample per step)"}
+        cfg = {"workload": ("C3 mixed ensemble of 1M nuclei over the nine preset isotopes, decay on, "
+                            "sharded by nucleus" if args.workload == "mixed" else
+                            "C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one nucleus per "
+                            "thread block")}
         extra = {"nucleus_steps_per_s": float(np.mean([n for _, n, _ in vals]))}
     line = {
         "impl": "reference", "metric": "pair interactions/s", "value": value, "unit": "pairs/s",
@@ -352,7 +363,9 @@ def main():
                     "chunks": runner.n_chunks},
             "roofline": {"bound": "fp32", "achieved": my_rate * flops_pair / 1e12, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": my_rate * flops_pair / 1e12 / fp32_peak,
-                         "traffic": None, "kernel": "ensemble_kernel",
+                         "traffic": ncu_traffic("ensemble_pair_kernel") if args.workload == "ensemble"
+                         and not args.nuclei and args.substeps == 1 else None,
+                         "kernel": "ensemble_pair_kernel",
                          "flops_per_pair": flops_pair,
                          "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
                                         "f32x2 %.1f TFLOP/s); nominal %.1f" % (f1.value, f2.value, nominal),

@@ -195,6 +195,19 @@ typedef struct {
  */
 int pyqmd_ensemble_step(const pyqmd_ensemble *e, int32_t n_steps, void *stream);
 
+/*
+ * Per-frame overlap projection of every listed nucleus: NuclearSimulation.resolve_overlaps,
+ * nuclear_sim.py:355-379 (sequential i < j sweep, minimum distance 5.0, immediate updates), run
+ * once per frame after the sub-steps (:175-176).  Only pos / offset / count / list / cap /
+ * id_base / seed / step0 of the descriptor are read.  `uniforms` (optional,
+ * double[n_nuclei][uniforms_per_nucleus], values in [0,1)) feeds the random direction of the
+ * degenerate case dist < 0.001 (:367-370) in consumption order; otherwise Philox(seed).
+ * `n_pushes` (optional device counter) accumulates the number of pushes applied.
+ */
+int pyqmd_resolve_overlaps(const pyqmd_ensemble *e, const double *uniforms,
+                           int32_t uniforms_per_nucleus, unsigned long long *n_pushes,
+                           void *stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* (D) decay-only population of particle-less nuclei (decay_chains.py:390-421; config 5)     */
 

@@ -66,6 +66,9 @@ def lib():
                                        C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int64,
                                        _f64p, _f64p, C.c_int]
         L.orc_cloud_forces.restype = None
+        L.orc_resolve_overlaps.argtypes = [C.c_int64, _f64p, _f64p, C.c_void_p, C.c_int64,
+                                           C.POINTER(C.c_int64)]
+        L.orc_resolve_overlaps.restype = C.c_int64
         L.orc_decay_probability.argtypes = [C.c_double, C.c_double]
         L.orc_decay_probability.restype = C.c_double
         L.orc_decay_decisions.argtypes = [C.c_int64, _f64p, C.c_double, _f64p, _u8p, C.c_void_p,
@@ -139,6 +142,17 @@ def cloud_forces(x, y, is_proton, i0, i1, S=150.0, Cc=30.0, P=35.0, center=None,
     fy = np.empty(i1 - i0)
     lib().orc_cloud_forces(n, x, y, t, S, Cc, P, center[0], center[1], i0, i1, fx, fy, n_threads)
     return fx, fy
+
+
+def resolve_overlaps(x, y, uniforms=()):
+    """nuclear_sim.py:355-379 on float64 arrays, in place.  Returns (draws consumed, pushes)."""
+    u = np.ascontiguousarray(uniforms, np.float64)
+    pushes = C.c_int64(0)
+    used = lib().orc_resolve_overlaps(len(x), x, y, _p(u) if len(u) else None, len(u),
+                                      C.byref(pushes))
+    if used < 0:
+        raise ValueError("resolve_overlaps needed more uniforms than supplied")
+    return int(used), int(pushes.value)
 
 
 def decay_probability(T, dt):

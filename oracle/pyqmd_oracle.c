@@ -276,6 +276,48 @@ void orc_cloud_forces(int64_t n, const double *x, const double *y, const uint8_t
 }
 
 /*
+ * Per-frame overlap projection; follows NuclearSimulation.resolve_overlaps,
+ * nuclear_sim.py:355-379: sequential Gauss-Seidel over i < j with immediate updates, minimum
+ * distance 5.0 (= 2 * radius).  The degenerate case dist < 0.001 (:367-370) draws
+ * random.uniform(0, 2*pi); the draws are taken in order from `uniforms` (as u in [0,1)).
+ * Returns the number of draws consumed, or -1 if `uniforms` ran out.
+ */
+int64_t orc_resolve_overlaps(int64_t n, double *x, double *y, const double *uniforms,
+                             int64_t n_uniforms, int64_t *n_pushes)
+{
+    const double min_dist = 5.0;                         /* :357 */
+    int64_t used = 0, pushes = 0;
+    for (int64_t i = 0; i < n; ++i) {                    /* :359 */
+        for (int64_t j = i + 1; j < n; ++j) {            /* :360 */
+            double dx = x[j] - x[i];                     /* :361 */
+            double dy = y[j] - y[i];                     /* :362 */
+            double dist2 = dx * dx + dy * dy;            /* :363 */
+            if (dist2 < min_dist * min_dist) {           /* :365 */
+                double dist = sqrt(dist2);               /* :366 */
+                if (dist < 0.001) {                      /* :367 */
+                    if (used >= n_uniforms) return -1;
+                    double angle = 0.0 + (2.0 * 3.141592653589793 - 0.0) * uniforms[used++];  /* :368 */
+                    dx = cos(angle);                     /* :369 */
+                    dy = sin(angle);
+                    dist = 0.001;                        /* :370 */
+                } else {
+                    dx /= dist;                          /* :372 */
+                    dy /= dist;                          /* :373 */
+                }
+                double push = (min_dist - dist) * 0.5;   /* :375 */
+                x[i] -= dx * push;                       /* :376 */
+                y[i] -= dy * push;                       /* :377 */
+                x[j] += dx * push;                       /* :378 */
+                y[j] += dy * push;                       /* :379 */
+                ++pushes;
+            }
+        }
+    }
+    if (n_pushes) *n_pushes = pushes;
+    return used;
+}
+
+/*
  * Decay probability for one sub-step; follows Nucleus.should_decay,
  * particles.py:126-147 (identical copy at decay_chains.py:400-421).
  * Returns -1.0 for a stable nucleus (T = inf): the reference returns False *without*

@@ -303,9 +303,11 @@ cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict_
                    int64_t i0, int64_t i1, CloudWorkspace w, LawParams L, int far_enabled,
                    int tiles_per_seg)
 {
-    __shared__ __align__(16) float sx[kTile];
-    __shared__ __align__(16) float sy[kTile];
-    __shared__ __align__(16) float st[kTile];
+    // double-buffered j tiles: one barrier per tile (the store of tile t+1 goes to the other
+    // buffer while tile t is being consumed)
+    __shared__ __align__(16) float sxb[2][kTile];
+    __shared__ __align__(16) float syb[2][kTile];
+    __shared__ __align__(16) float stb[2][kTile];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t wbase = i0 + (int64_t)blockIdx.x * kIBlock + (int64_t)wid * (32 * kIPT);
@@ -355,15 +357,25 @@ cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict_
         const int64_t j = t_begin * kTile + threadIdx.x;
         if (j < n) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
     }
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
-        __syncthreads();                               // previous tile fully consumed
-        sx[threadIdx.x] = nxt.x;
-        sy[threadIdx.x] = nxt.y;
-        st[threadIdx.x] = nxt_t;
-        __syncthreads();
-        {
-            const int64_t j = (tile + 1) * kTile + threadIdx.x;
-            if (j < n && tile + 1 < t_end) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+    if (t_begin < t_end) {
+        sxb[0][threadIdx.x] = nxt.x;
+        syb[0][threadIdx.x] = nxt.y;
+        stb[0][threadIdx.x] = nxt_t;
+        const int64_t j = (t_begin + 1) * kTile + threadIdx.x;
+        if (j < n && t_begin + 1 < t_end) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+    }
+    int buf = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile, buf ^= 1) {
+        __syncthreads();              // tile `tile` is complete in buffer `buf`; buffer buf^1 is free
+        const float* sx = sxb[buf];
+        const float* sy = syb[buf];
+        const float* st = stb[buf];
+        if (tile + 1 < t_end) {
+            sxb[buf ^ 1][threadIdx.x] = nxt.x;
+            syb[buf ^ 1][threadIdx.x] = nxt.y;
+            stb[buf ^ 1][threadIdx.x] = nxt_t;
+            const int64_t j = (tile + 2) * kTile + threadIdx.x;
+            if (j < n && tile + 2 < t_end) { nxt = pos_in[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
         }
         const int64_t rem = n - tile * kTile;
         const int jmax = rem < kTile ? (int)rem : kTile;

@@ -217,6 +217,31 @@ class NucleusEnsemble:
         self.step_index += n_steps
         return len(self.bins)
 
+    def resolve_overlaps(self, uniforms=None):
+        """Per-frame projection NuclearSimulation.resolve_overlaps (nuclear_sim.py:355-379) for
+        every nucleus.  ``uniforms``: optional float64 [n_nuclei, k] draws for the degenerate
+        coincident-pair case.  Returns the device counter tensor of pushes applied so far."""
+        if not hasattr(self, "push_count"):
+            self.push_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        k = 0
+        if uniforms is not None:
+            uniforms = torch.as_tensor(uniforms, dtype=torch.float64).contiguous().to(self.device)
+            assert uniforms.shape[0] == self.n_nuclei
+            k = int(uniforms.shape[1])
+        lib = _lib.lib()
+        for cap, lst, n_list in self.bins:
+            d = self._desc(cap, lst, n_list, None)
+            _lib.check(lib.pyqmd_resolve_overlaps(C.byref(d), _lib.ptr(uniforms), k,
+                                                  self.push_count.data_ptr(),
+                                                  _lib.current_stream()), "pyqmd_resolve_overlaps")
+        return self.push_count
+
+    def frame(self, n_substeps=4, uniforms=None):
+        """One app frame (nuclear_sim.py:161-176): ``n_substeps`` sub-steps, then the overlap
+        projection."""
+        self.step(n_substeps, uniforms)
+        self.resolve_overlaps()
+
     def pairs_per_step(self):
         """Ordered pair interactions one sub-step evaluates: sum of A(A-1)."""
         c = self.count.to(torch.int64)

@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 1 --no-extras \
     > gpurun_out/ncu_launches_${TAG}.log 2>&1
 python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ensemble_kernel -s 1 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:ensemble -s 1 -c 1 \
     -f -o gpurun_out/prof_ensemble_${TAG} python bench.py --steps 2 --warmup 1 --no-extras \
     > gpurun_out/ncu_ens_${TAG}.log 2>&1
 python bench.py --workload cloud --cloud-n 262144 --steps 1 --warmup 1 > gpurun_out/plain3_${TAG}.log 2>&1 &&

@@ -11,6 +11,7 @@ Writes
   tests/golden/decay_tables.json.gz   get_half_life / get_decay_product over a (Z,N) grid
   tests/golden/decay_events.json.gz   should_decay probabilities, seeded decision strings,
                                       adjust_particles cases, decay-chain walks, sub-step loops
+  tests/golden/resolve_overlaps.json.gz  per-frame overlap projection (nuclear_sim.py:355-379)
   oracle/nuclide_data.json            HALF_LIVES / DECAY_CHAINS dump (oracle's copy)
   pyqmd_b200/data/nuclide_data.json   same dump (product's copy)
   pyqmd_b200/data/layout_templates.npz  reference-generated initial layouts (particles.py:62-124)
@@ -410,6 +411,67 @@ def gen_decay_events():
           len(adj), "adjust cases,", len(walks), "walks,", len(loops), "loops")
 
 
+def gen_resolve_overlaps():
+    """NuclearSimulation.resolve_overlaps (nuclear_sim.py:355-379) on reference nuclei: fresh
+    layouts, layouts after force steps, and a frame loop (4 sub-steps + projection per frame,
+    nuclear_sim.py:161-176)."""
+    import importlib
+    ns = importlib.import_module("nuclear_sim")
+    pm = R.particles
+    sim = object.__new__(ns.NuclearSimulation)
+    nf = R.forces()
+    cases = []
+
+    def project(ps, draws=()):
+        nuc = object.__new__(pm.Nucleus)
+        nuc.particles = ps
+        sim.nucleus = nuc
+        fd = ref_loader.DrawFeeder(list(draws))
+        ns.random = fd
+        sim.resolve_overlaps()
+        ns.random = random
+        return fd.used
+
+    for (z, n), seed, pre_steps in (((6, 8), 1, 0), ((2, 2), 2, 0), ((26, 30), 3, 0), ((26, 30), 3, 6),
+                                    ((82, 126), 4, 0), ((82, 126), 4, 10), ((92, 146), 5, 3),
+                                    ((1, 0), 6, 0)):
+        random.seed(seed)
+        nuc = pm.Nucleus(z, n, 0.0, 0.0)
+        ps = nuc.particles
+        for p in ps:
+            p.x, p.y = float(np.float32(p.x)), float(np.float32(p.y))
+        for _ in range(pre_steps):
+            nf.update_particles_cpu(ps, 1 / 240)
+        for p in ps:                              # FP32-representable input for the device side
+            p.x, p.y = float(np.float32(p.x)), float(np.float32(p.y))
+        inp = state_of(ps)
+        used = project(ps)
+        cases.append(dict(name=f"z{z}n{n}_pre{pre_steps}", input=inp, output=state_of(ps), used=used,
+                          draws=[]))
+    # degenerate pair (dist < 0.001) consumes one draw
+    ps = R.make_particles([0.0, 0.0002, 3.0], [0.0, 0.0003, 0.5], [0] * 3, [0] * 3, [1, 0, 1])
+    inp = state_of(ps)
+    used = project(ps, [0.3125])
+    cases.append(dict(name="degenerate", input=inp, output=state_of(ps), used=used, draws=[hx(0.3125)]))
+    # frame loop: 4 force sub-steps then one projection, 12 frames (no decay)
+    random.seed(9)
+    nuc = pm.Nucleus(26, 30, 0.0, 0.0)
+    ps = nuc.particles
+    for p in ps:
+        p.x, p.y = float(np.float32(p.x)), float(np.float32(p.y))
+    frames = [state_of(ps)]
+    for f in range(12):
+        for _ in range(4):
+            nf.update_particles_cpu(ps, 1 / 240)
+        project(ps)
+        frames.append(state_of(ps))
+    with gzip.open(os.path.join(GOLD, "resolve_overlaps.json.gz"), "wt") as f:
+        json.dump(dict(source="NuclearSimulation.resolve_overlaps nuclear_sim.py:355-379; frame loop "
+                              ":161-176", cases=cases, frames=frames, substeps_per_frame=4,
+                       dt=hx(1 / 240)), f, separators=(",", ":"))
+    print("resolve_overlaps:", len(cases), "cases,", len(frames) - 1, "frames")
+
+
 def check_handle_decay_slice():
     """Sanity: the physics slice used above equals the real NuclearSimulation.handle_decay
     (nuclear_sim.py:212-353) in Z, N, particle list, centre and stability."""
@@ -449,7 +511,7 @@ def check_handle_decay_slice():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["data", "kats", "tables", "events", "check", "layouts", "traj"]
+    what = sys.argv[1:] or ["data", "kats", "tables", "events", "check", "overlaps", "layouts", "traj"]
     if "data" in what:
         gen_nuclide_data()
     if "kats" in what:
@@ -460,6 +522,8 @@ if __name__ == "__main__":
         gen_decay_events()
     if "check" in what:
         check_handle_decay_slice()
+    if "overlaps" in what:
+        gen_resolve_overlaps()
     if "layouts" in what:
         gen_layouts()
     if "traj" in what:

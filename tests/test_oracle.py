@@ -271,3 +271,25 @@ def test_live_against_reference():
     assert np.array_equal(x, np.array([p.x for p in ps]))
     assert np.array_equal(vy, np.array([p.vy for p in ps]))
     assert orc.py312_mean(x) == sum(p.x for p in ps) / len(ps)
+
+
+def test_resolve_overlaps_bit_exact():
+    """Per-frame projection nuclear_sim.py:355-379, incl. the degenerate pair and the frame loop
+    (4 sub-steps + projection, :161-176)."""
+    from conftest import load_json
+    g = load_json("resolve_overlaps.json.gz")
+    for case in g["cases"]:
+        x, y = unhex(case["input"]["x"]).copy(), unhex(case["input"]["y"]).copy()
+        used, pushes = orc.resolve_overlaps(x, y, [float.fromhex(h) for h in case["draws"]])
+        assert used == case["used"], case["name"]
+        assert np.array_equal(x, unhex(case["output"]["x"])), case["name"]
+        assert np.array_equal(y, unhex(case["output"]["y"])), case["name"]
+    f0 = g["frames"][0]
+    x, y = unhex(f0["x"]).copy(), unhex(f0["y"]).copy()
+    vx, vy = unhex(f0["vx"]).copy(), unhex(f0["vy"]).copy()
+    t = np.array(f0["is_proton"], np.uint8)
+    for k, fr in enumerate(g["frames"][1:]):
+        for _ in range(g["substeps_per_frame"]):
+            orc.force_step(x, y, vx, vy, t, float.fromhex(g["dt"]))
+        orc.resolve_overlaps(x, y)
+        assert np.array_equal(x, unhex(fr["x"])) and np.array_equal(vy, unhex(fr["vy"])), k
