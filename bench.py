@@ -16,7 +16,7 @@ Contract (one JSON line from rank 0):
            every step
   roofline dominant kernel vs the FP32 FMA peak measured in this run (FFMA-chain
            microbenchmark; MEASURED_PEAKS.json has no FP32 figure), algorithmic FLOPs per
-           pair by SURVEY.md section 8(d)'s convention counted by the oracle on a sample of the state
+           pair by SURVEY.md section 8(d)'s convention from a device-side branch census of the state
   cpu_baseline  the oracle's C port (OpenMP, all host cores) on a bounded sample, rank 0, N=1
   also     (unless --no-extras) the single-cloud workload of configs[3] (N = 1M nucleons,
            i-block sharded + position all-gather, "strong" scaling) measured in the same run
@@ -100,6 +100,13 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.05)
 
+    def sample_once(self):
+        if self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
+
     def result(self):
         self.stop_flag = True
         if self.nv is None or not self.samples:
@@ -128,22 +135,6 @@ def physical_gpu_index(local_rank):
 
 
 # ---------------------------------------------------------------------------------------------
-def oracle_sample_flops(pos, isp, counts, offsets, sample):
-    """Algorithmic FLOPs per ordered pair (SURVEY.md section 8d convention) on sampled nuclei."""
-    from oracle import oracle as orc
-    flops = pairs = 0
-    for k in sample:
-        o, c = int(offsets[k]), int(counts[k])
-        if c < 2:
-            continue
-        x = pos[o:o + c, 0].astype(np.float64); y = pos[o:o + c, 1].astype(np.float64)
-        r = orc.force_step(x, y, np.zeros(c), np.zeros(c), isp[o:o + c], 1 / 240, integrate=False,
-                           want_stats=True)
-        flops += r["stats"].flops()
-        pairs += c * (c - 1)
-    return flops / max(pairs, 1)
-
-
 def cpu_ensemble_sample(isotopes, n_nuclei, n_steps, threads):
     """(pairs/s, nucleus-steps/s, seconds) of the oracle port on n_nuclei template nuclei."""
     from oracle import oracle as orc
@@ -257,6 +248,8 @@ def timed_steps(fn, steps, warmup, dist, torch, sampler=None):
     for _ in range(steps):
         fn()
     e1.record()
+    if sampler is not None:
+        sampler.sample_once()         # the queue is still draining: a sample under load even for short runs
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -326,15 +319,12 @@ def main():
                                              dt_decay=180825048000.0 * 1e-3, seed=2024)
         pairs_step = ens.pairs_per_step() * args.substeps
         nucleons = int(ens.count.sum().item())
-        flops0 = oracle_sample_flops(ens.pos.cpu().numpy(), ens.is_proton.cpu().numpy(),
-                                     ens.count.cpu().numpy(), ens.offsets.cpu().numpy(),
-                                     range(0, ens.n_nuclei, max(1, ens.n_nuclei // 32))) if rank == 0 else 0
+        sample = range(0, ens.n_nuclei, max(1, ens.n_nuclei // 256))
+        flops0 = ens.census(sample)[1]
         sec = timed_steps(lambda: ens.step(args.substeps), K, W, dist, torch, sampler)
         clocks = sampler.result()
         launches = K * len(ens.bins)
-        flops1 = oracle_sample_flops(ens.pos.cpu().numpy(), ens.is_proton.cpu().numpy(),
-                                     ens.count.cpu().numpy(), ens.offsets.cpu().numpy(),
-                                     range(0, ens.n_nuclei, max(1, ens.n_nuclei // 32))) if rank == 0 else 0
+        census1, flops1 = ens.census(sample)
         tot_pairs = torch.tensor([float(pairs_step)], device=dev, dtype=torch.float64)
         tot_nuc = torch.tensor([float(ens.n_nuclei)], device=dev, dtype=torch.float64)
         if dist is not None:
@@ -366,7 +356,7 @@ def main():
                          "traffic": ncu_traffic("ensemble_pair_kernel") if args.workload == "ensemble"
                          and not args.nuclei and args.substeps == 1 else None,
                          "kernel": "ensemble_pair_kernel",
-                         "flops_per_pair": flops_pair,
+                         "flops_per_pair": flops_pair, "branch_census_end": census1,
                          "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
                                         "f32x2 %.1f TFLOP/s); nominal %.1f" % (f1.value, f2.value, nominal),
                          "hbm_gbs": nucleons * 36 * args.substeps * K / sec / 1e9 / max(args.substeps, 1),
@@ -386,9 +376,18 @@ def main():
     line["gpu_launches"] = launches
 
     if not args.no_extras and args.workload == "ensemble":
+        # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection
+        for _ in range(3):
+            ens.frame(4)
+        sec_f = timed_steps(lambda: ens.frame(4), 5, 1, dist, torch)
+        frame = {"ms_per_frame": sec_f / 5 * 1e3, "substeps_per_frame": 4,
+                 "nucleus_frames_per_s": float(tot_nuc.item()) * 5 / sec_f,
+                 "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 5 / sec_f,
+                 "note": "4 sub-steps + resolve_overlaps per frame, device resident"}
         extra = bench_cloud(args, 2, 1, rank, world, dev, dist, torch, None, fp32_peak,
                             (f1.value, f2.value, nominal))
-        line["also"] = {"cloud": {k: extra[k] for k in ("value", "ms_per_step", "config", "roofline",
+        line["also"] = {"frame": frame,
+                        "cloud": {k: extra[k] for k in ("value", "ms_per_step", "config", "roofline",
                                                         "scaling")}}
 
     if rank == 0 and world == 1:

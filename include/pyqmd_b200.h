@@ -208,6 +208,13 @@ int pyqmd_resolve_overlaps(const pyqmd_ensemble *e, const double *uniforms,
                            int32_t uniforms_per_nucleus, unsigned long long *n_pushes,
                            void *stream);
 
+/*
+ * Branch census of the pair law over every ordered pair of the listed nuclei
+ * (nuclear_forces.py:257-291), for the algorithmic-FLOP accounting of the roofline; accumulates
+ * into counts[8] (device): evaluated, skipped, hard core, core, attractive, tail, p-p, Pauli.
+ */
+int pyqmd_ensemble_census(const pyqmd_ensemble *e, unsigned long long *counts, void *stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* (D) decay-only population of particle-less nuclei (decay_chains.py:390-421; config 5)     */
 

@@ -24,7 +24,8 @@ EXPORTS = (
     "pyqmd_fp32_peak",
     "pyqmd_update_forces_and_positions", "pyqmd_update_particles_f64",
     "pyqmd_cloud_workspace_bytes", "pyqmd_cloud_step", "pyqmd_cloud_sort_keys",
-    "pyqmd_ensemble_step", "pyqmd_resolve_overlaps", "pyqmd_population_step",
+    "pyqmd_ensemble_step", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
+    "pyqmd_population_step",
 )
 
 # numpy mirror of pyqmd_nuclide_entry (80 bytes)
@@ -99,6 +100,7 @@ def lib():
     L.pyqmd_cloud_sort_keys.argtypes = [vp, vp, i64, f32, f32, f32, vp, vp]
     L.pyqmd_ensemble_step.argtypes = [C.POINTER(EnsembleDesc), i32, vp]
     L.pyqmd_resolve_overlaps.argtypes = [C.POINTER(EnsembleDesc), vp, i32, vp, vp]
+    L.pyqmd_ensemble_census.argtypes = [C.POINTER(EnsembleDesc), vp, vp]
     L.pyqmd_population_step.argtypes = [C.POINTER(PopulationDesc), i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -92,9 +92,61 @@ resolve_overlaps_kernel(const pyqmd_ensemble e, const double* __restrict__ unifo
     if (n_pushes && lane == 0 && pushes) atomicAdd(n_pushes, pushes);
 }
 
+// ---- branch census -----------------------------------------------------------------------------------
+// Counts, for every ordered pair of the listed nuclei, which branches of the law
+// (nuclear_forces.py:257-291) it takes.  Used for the algorithmic-FLOP accounting of the roofline
+// (15 per evaluated pair + 4/7/8 core/attractive/tail + 5 hard core + 3 p-p
+// + 6 Pauli); not on the hot path.
+// counts: [0] evaluated, [1] skipped (d2 < 0.01), [2] hard, [3] core, [4] attractive, [5] tail,
+//         [6] p-p, [7] Pauli
+__global__ void __launch_bounds__(256) census_kernel(const pyqmd_ensemble e,
+                                                     unsigned long long* __restrict__ counts)
+{
+    __shared__ unsigned long long sc[8];
+    if (threadIdx.x < 8) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t q = blockIdx.x;
+    const int nuc = e.list ? e.list[q] : (int)q;
+    const int cnt = e.count[nuc];
+    const float2* pos = reinterpret_cast<const float2*>(e.pos) + e.offset[nuc];
+    const uint8_t* isp = e.is_proton + e.offset[nuc];
+    unsigned c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t p = threadIdx.x; p < (int64_t)cnt * cnt; p += blockDim.x) {
+        const int i = (int)(p / cnt), j = (int)(p % cnt);
+        if (i == j) continue;
+        const float dx = pos[j].x - pos[i].x, dy = pos[j].y - pos[i].y;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 < 0.01f) { ++c[1]; continue; }
+        ++c[0];
+        if (d2 < 4.25f * 4.25f) ++c[2];
+        if (d2 < 2.8f * 2.8f) ++c[3];
+        else if (d2 < 81.0f) ++c[4];
+        else ++c[5];
+        if (isp[i] && isp[j]) ++c[6];
+        if ((isp[i] != 0) == (isp[j] != 0) && d2 < 64.0f) ++c[7];
+    }
+    for (int k = 0; k < 8; ++k)
+        if (c[k]) atomicAdd(&sc[k], (unsigned long long)c[k]);
+    __syncthreads();
+    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, sc[threadIdx.x]);
+}
+
 }  // namespace pyqmd
 
 using namespace pyqmd;
+
+extern "C" int pyqmd_ensemble_census(const pyqmd_ensemble* e, unsigned long long* counts,
+                                     void* stream)
+{
+    PYQMD_REQUIRE(e != nullptr && counts != nullptr, "NULL argument");
+    PYQMD_REQUIRE(e->pos && e->is_proton && e->offset && e->count, "state arrays");
+    const int64_t n_list = e->list ? e->n_list : e->n_nuclei;
+    if (n_list == 0) return PYQMD_OK;
+    PYQMD_REQUIRE(n_list <= 2147483647LL, "too many nuclei for one launch");
+    census_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(*e, counts);
+    PYQMD_CUDA_CHECK(cudaGetLastError());
+    return PYQMD_OK;
+}
 
 extern "C" int pyqmd_resolve_overlaps(const pyqmd_ensemble* e, const double* uniforms,
                                       int32_t uniforms_per_nucleus, unsigned long long* n_pushes,

@@ -1,0 +1,217 @@
+"""Headless, GPU-resident counterpart of the physics half of ``NuclearSimulation``
+(OtsoBear/PyQMD nuclear_sim.py:31-176, 178-210, 212-353) for N nuclei at once: the caller side
+of the hot path, without pygame.
+
+    sim = HeadlessSimulation((92, 146), n_nuclei=4096)
+    sim.time_scale = 3.15576e16                 # 'billion' preset, nuclear_sim.py:86
+    for _ in range(600):
+        sim.update_simulation(1 / 60)           # one frame: sub-steps + overlap projection
+    sim.decay_counts                            # populated (the reference never increments it)
+    sim.free_particles                          # emitted alpha/e-/e+/gamma still alive
+
+Frame logic mirrored here, on the host, with the reference's formulas:
+  sub-step plan                    nuclear_sim.py:123-153   -> ``substep_plan``
+  sub-step loop                    :161-173                 -> NucleusEnsemble.step (device)
+  overlap projection once a frame  :175-176, :355-379       -> NucleusEnsemble.resolve_overlaps
+  emitted particle speed/lifetime  :295-342                 -> ``cosmetic_speed_lifetime``
+  free particle animation          :178-210                 -> ``animate``
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .types import DecayType, ParticleType
+
+_ANIMATED = (ParticleType.ALPHA.value, ParticleType.ELECTRON.value, ParticleType.GAMMA.value,
+             ParticleType.POSITRON.value)
+_DEFAULT_LIFETIME = {ParticleType.ALPHA.value: 2.0, ParticleType.ELECTRON.value: 3.0,
+                     ParticleType.GAMMA.value: 1.0, ParticleType.POSITRON.value: 3.0}  # particles.py:31-38
+
+#: nuclear_sim.py:78-87
+TIME_SCALE_PRESETS = {
+    "real": 1.0, "minute": 60.0, "hour": 3600.0, "day": 86400.0, "year": 31557600.0,
+    "millennium": 31557600000.0, "million": 31557600000000.0, "billion": 31557600000000000.0,
+}
+
+
+def substep_plan(dt, time_scale, physics_dt=1.0 / 240.0, accuracy=1, max_substeps=20,
+                 auto_adjust_substeps=False, physics_dt_factor=0.8):
+    """Sub-step plan of update_simulation (nuclear_sim.py:123-153).
+
+    Returns (num_steps, effective_physics_dt, step_time, physics_dt) where ``step_time`` is the dt
+    should_decay sees (:165) and ``effective_physics_dt`` the dt of the force step (:171)."""
+    desired_dt = dt * time_scale                                            # :123
+    if auto_adjust_substeps and time_scale != 1.0:                          # :131-142
+        if time_scale > 1.0:
+            scale = min(10.0, time_scale ** 0.3)
+            physics_dt = min(1.0 / 60.0, physics_dt_factor * scale / 240.0)
+        else:
+            scale = max(0.1, time_scale ** 0.2)
+            physics_dt = max(1.0 / 1000.0, physics_dt_factor * scale / 240.0)
+    effective = physics_dt * (2.0 - accuracy)                               # :145
+    factor = 1.0 if time_scale <= 10.0 else math.log10(time_scale)          # :149
+    cap = int(max_substeps * factor) if auto_adjust_substeps else max_substeps   # :150
+    num_steps = max(1, min(cap, int(desired_dt / effective)))               # :153
+    return num_steps, effective, desired_dt / num_steps, physics_dt
+
+
+def cosmetic_speed_lifetime(ptype, vx, vy, time_scale, substeps_used, physics_dt):
+    """Speed renormalisation and lifetime of a freshly emitted particle (nuclear_sim.py:295-342).
+    ``ptype`` is a ParticleType value; returns (vx, vy, lifetime)."""
+    if ptype == ParticleType.ALPHA.value:
+        base_speed = 30.0
+    elif ptype == ParticleType.GAMMA.value:
+        base_speed = 60.0
+    elif ptype in (ParticleType.ELECTRON.value, ParticleType.POSITRON.value):
+        base_speed = 50.0
+    else:
+        base_speed = 40.0
+    mag = math.sqrt(vx ** 2 + vy ** 2)
+    if mag > 0.001:
+        vx, vy = (vx / mag) * base_speed, (vy / mag) * base_speed
+    base_lifetime = 5.0
+    if time_scale > 1.0:
+        ts_factor = max(1.0, time_scale / 100.0)
+        sub_factor = max(1.0, math.sqrt(substeps_used))
+        dt_factor = max(1.0, 0.016 / physics_dt)
+        lifetime = max(base_lifetime * sub_factor, base_lifetime * (ts_factor * sub_factor * dt_factor))
+        if substeps_used > 15:
+            lifetime *= substeps_used / 15.0
+    else:
+        default = _DEFAULT_LIFETIME.get(ptype, float("inf"))
+        lifetime = max(default, base_lifetime * max(1.0, substeps_used / 5.0))
+    return vx, vy, lifetime
+
+
+def animate(ptype, x, y, vx, vy, age, lifetime, dt, age_dt, time_scale, substeps_used):
+    """One update_particle call (nuclear_sim.py:178-210) on arrays; returns (x, y, age, alive)."""
+    ptype = np.asarray(ptype)
+    animated = np.isin(ptype, _ANIMATED)
+    speed_scale = 0.3 * (10.0 / max(1.0, substeps_used))
+    aging = min(1.0, 1.0 / (math.sqrt(max(1.0, time_scale / 100.0)) *
+                            math.sqrt(max(1.0, substeps_used / 10.0))))
+    step_n = dt * (time_scale ** 0.5)
+    # same association as the reference: (v * ANIMATION_DT) * SPEED_SCALE  (:194-195)
+    x = np.where(animated, x + vx * (1.0 / 240.0) * speed_scale, x + vx * step_n)
+    y = np.where(animated, y + vy * (1.0 / 240.0) * speed_scale, y + vy * step_n)
+    age = np.where(animated, age + age_dt * aging, age + age_dt)
+    alive = np.where(animated, age < lifetime, True)
+    return x, y, age, alive
+
+
+class HeadlessSimulation:
+    """N copies of the reference's single-nucleus simulation, stepped frame by frame on the GPU."""
+
+    def __init__(self, isotope=(92, 146), n_nuclei=1, *, isotopes=None, device="cuda", seed=0,
+                 time_scale=1.0, origin=(400.0, 400.0), rotate=True):
+        from .state import NucleusEnsemble
+        self.isotopes = tuple(isotopes) if isotopes else (tuple(isotope),)
+        self.physics_dt = 1.0 / 240.0           # nuclear_sim.py:59
+        self.accuracy = 1                       # :62
+        self.max_substeps = 20                  # :63
+        self.auto_adjust_substeps = False       # :65
+        self.physics_dt_factor = 0.8            # :66
+        self.time_scale = float(time_scale)     # :50
+        self.time_passed = 0.0                  # :54
+        self.substeps_used = 0                  # :64
+        self.frames = 0
+        self.decay_counts = {d.name: 0 for d in DecayType if d != DecayType.NONE}   # :56
+        org = np.tile(np.asarray(origin, np.float64), (n_nuclei, 1))                # :93
+        self.ensemble = NucleusEnsemble.from_templates(self.isotopes, n_nuclei, device=device,
+                                                       seed=seed, origin=org, rotate=rotate,
+                                                       dt_decay=1.0 / 240.0)
+        self._events_seen = 0
+        # free (emitted) particles, SoA on the host: few and short-lived
+        self.free = {k: np.zeros(0) for k in ("x", "y", "vx", "vy", "age", "lifetime")}
+        self.free["type"] = np.zeros(0, np.int32)
+        self.free["nucleus"] = np.zeros(0, np.int64)
+
+    @property
+    def free_particles(self):
+        return self.free
+
+    def update_simulation(self, dt):
+        """One frame (nuclear_sim.py:118-176)."""
+        num_steps, eff_dt, step_time, self.physics_dt = substep_plan(
+            dt, self.time_scale, self.physics_dt, self.accuracy, self.max_substeps,
+            self.auto_adjust_substeps, self.physics_dt_factor)
+        self.time_passed += dt * self.time_scale                            # :124
+        self.substeps_used = num_steps                                      # :154
+        ens = self.ensemble
+        ens.dt_phys = eff_dt
+        ens.set_dt_decay(step_time)
+        step0 = ens.step_index
+        ens.step(num_steps)                                                 # :161-173
+        ens.resolve_overlaps()                                              # :175-176
+        # free particles already alive: one animation update per sub-step (:162)
+        self.free = self._animate(self.free, num_steps, eff_dt, step_time, num_steps)
+        # this frame's emissions (:349): a particle emitted in sub-step s is animated by the
+        # remaining sub-steps s+1 .. num_steps-1 of the frame
+        self._collect_events(num_steps, step0, eff_dt, step_time)
+        self.frames += 1
+
+    def _animate(self, f, n_updates, eff_dt, step_time, num_steps):
+        n_updates = np.broadcast_to(np.asarray(n_updates), f["x"].shape)
+        for k in range(int(n_updates.max()) if len(f["x"]) else 0):
+            x, y, age, alive = animate(f["type"], f["x"], f["y"], f["vx"], f["vy"], f["age"],
+                                       f["lifetime"], eff_dt, step_time, self.time_scale, num_steps)
+            todo = n_updates > k
+            f["x"] = np.where(todo, x, f["x"])
+            f["y"] = np.where(todo, y, f["y"])
+            f["age"] = np.where(todo, age, f["age"])
+            keep = alive | ~todo
+            if not keep.all():
+                f = {key: v[keep] for key, v in f.items()}
+                n_updates = n_updates[keep]
+        return f
+
+    def _collect_events(self, num_steps, step0=0, eff_dt=1.0 / 240.0, step_time=1.0 / 240.0):
+        ens = self.ensemble
+        total = int(ens.event_count.item())
+        mc = ens.mode_counts.cpu().tolist()
+        for d in DecayType:
+            if d != DecayType.NONE:
+                self.decay_counts[d.name] = int(mc[d.value])
+        if total == self._events_seen:
+            return
+        ev = ens.events()
+        ev = ev[np.argsort(ev["step"], kind="stable")]
+        new = ev[self._events_seen:] if len(ev) >= total else ev[-(total - self._events_seen):]
+        self._events_seen = total
+        new = new[new["ptype"] >= 0]
+        if len(new) == 0:
+            return
+        vx, vy, life = [], [], []
+        for e in new:
+            a, b, c = cosmetic_speed_lifetime(int(e["ptype"]), float(e["vx"]), float(e["vy"]),
+                                              self.time_scale, num_steps, self.physics_dt)
+            vx.append(a); vy.append(b); life.append(c)
+        born = dict(x=new["x"].astype(np.float64), y=new["y"].astype(np.float64),
+                    vx=np.array(vx), vy=np.array(vy), age=np.zeros(len(new)),
+                    lifetime=np.array(life), type=new["ptype"].astype(np.int32),
+                    nucleus=new["nucleus"].astype(np.int64))
+        remaining = np.clip(num_steps - 1 - (new["step"].astype(np.int64) - step0), 0, num_steps)
+        born = self._animate(born, remaining, eff_dt, step_time, num_steps)
+        self.free = {k: np.concatenate([self.free[k], born[k]]) for k in self.free}
+
+    def nucleus_view(self, k=0):
+        """A ``Nucleus`` (pyqmd_b200.types) materialised from the device state of nucleus ``k`` --
+        the render bridge: ``Renderer`` reads ``.particles[i].x/.y/.type/.radius`` and
+        ``.protons/.neutrons/.stability`` (rendering.py:42-48, 135-246)."""
+        from .types import Nucleus, Particle
+        ens = self.ensemble
+        o, c = int(ens.offsets[k]), int(ens.count[k])
+        pos = ens.pos[o:o + c].cpu().numpy().astype(np.float64)
+        vel = ens.vel[o:o + c].cpu().numpy().astype(np.float64)
+        isp = ens.is_proton[o:o + c].cpu().numpy()
+        org = ens.origin[k].cpu().numpy() if ens.origin is not None else np.zeros(2)
+        ps = [Particle(float(p[0] + org[0]), float(p[1] + org[1]),
+                       ParticleType.PROTON if t else ParticleType.NEUTRON, float(v[0]), float(v[1]))
+              for p, v, t in zip(pos, vel, isp)]
+        zn = int(ens.zn[k])
+        nuc = Nucleus(zn >> 16, zn & 0xFFFF, float(org[0]), float(org[1]), particles=ps)
+        nuc.update_center_of_mass()
+        nuc.stability = float(ens.half_life[k])
+        return nuc

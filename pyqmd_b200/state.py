@@ -50,6 +50,8 @@ def layout_templates():
 def device_table(dt_decay: float, device) -> torch.Tensor:
     key = (float(dt_decay), str(device))
     if key not in _TABLE_CACHE:
+        while len(_TABLE_CACHE) >= 8:           # dt varies per frame in the app: bounded cache
+            _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
         tab = nuclides.build_device_table(dt_decay)
         _TABLE_CACHE[key] = torch.from_numpy(tab.view(np.uint8).copy()).to(device)
     return _TABLE_CACHE[key]
@@ -197,6 +199,21 @@ class NucleusEnsemble:
         d.event_count, d.mode_counts = self.event_count.data_ptr(), self.mode_counts.data_ptr()
         return d
 
+    def set_dt_decay(self, dt_decay):
+        """Change the dt ``should_decay`` sees (nuclear_sim.py:165: it varies from frame to frame
+        with the time scale).  Per-nucleus probabilities are recomputed on the host from the
+        current half-lives with the reference's expression (particles.py:134-144) and libm, one
+        evaluation per distinct half-life, so decisions stay bit-exact."""
+        dt_decay = float(dt_decay)
+        if dt_decay == self.dt_decay:
+            return
+        self.dt_decay = dt_decay
+        self.table = device_table(dt_decay, self.device)
+        uniq, inv = torch.unique(self.half_life, return_inverse=True)
+        pu = np.array([nuclides.decay_probability(float(t), dt_decay) for t in uniq.cpu().tolist()],
+                      np.float64)
+        self.p_decay.copy_(torch.from_numpy(pu).to(self.device)[inv])
+
     def launch(self, cap, lst_ptr, n_list, n_steps, stream, uniforms=None):
         d = self._desc(cap, None, n_list, uniforms)
         d.list = lst_ptr
@@ -241,6 +258,29 @@ class NucleusEnsemble:
         projection."""
         self.step(n_substeps, uniforms)
         self.resolve_overlaps()
+
+    def census(self, sample=None):
+        """Branch census of the pair law (device kernel) over ``sample`` (iterable of nucleus
+        indices, default all).  Returns (counts dict, algorithmic FLOPs per ordered pair by the
+        convention of SURVEY.md section 8d)."""
+        counts = torch.zeros(8, dtype=torch.int64, device=self.device)
+        lib = _lib.lib()
+        if sample is None:
+            todo = [(cap, lst, n) for cap, lst, n in self.bins]
+            keep = []
+        else:
+            lst = torch.as_tensor(list(sample), dtype=torch.int32, device=self.device)
+            todo, keep = [(1024, lst, int(lst.numel()))], [lst]
+        for cap, lst, n_list in todo:
+            d = self._desc(cap, lst, n_list, None)
+            _lib.check(lib.pyqmd_ensemble_census(C.byref(d), counts.data_ptr(),
+                                                 _lib.current_stream()), "pyqmd_ensemble_census")
+        c = counts.cpu().tolist()
+        names = ("evaluated", "skipped", "hard", "core", "attr", "tail", "pp", "pauli")
+        out = dict(zip(names, c))
+        flops = (15 * c[0] + 5 * c[2] + 4 * c[3] + 7 * c[4] + 8 * c[5] + 3 * c[6] + 6 * c[7])
+        pairs = c[0] + c[1]
+        return out, (flops / pairs if pairs else 0.0)
 
     def pairs_per_step(self):
         """Ordered pair interactions one sub-step evaluates: sum of A(A-1)."""

@@ -12,6 +12,7 @@ Writes
   tests/golden/decay_events.json.gz   should_decay probabilities, seeded decision strings,
                                       adjust_particles cases, decay-chain walks, sub-step loops
   tests/golden/resolve_overlaps.json.gz  per-frame overlap projection (nuclear_sim.py:355-379)
+  tests/golden/sim_driver.json.gz     sub-step plan, emitted-particle cosmetics and animation
   oracle/nuclide_data.json            HALF_LIVES / DECAY_CHAINS dump (oracle's copy)
   pyqmd_b200/data/nuclide_data.json   same dump (product's copy)
   pyqmd_b200/data/layout_templates.npz  reference-generated initial layouts (particles.py:62-124)
@@ -472,6 +473,84 @@ def gen_resolve_overlaps():
     print("resolve_overlaps:", len(cases), "cases,", len(frames) - 1, "frames")
 
 
+def gen_sim_driver():
+    """Frame-level host logic of NuclearSimulation: the sub-step plan of update_simulation
+    (nuclear_sim.py:123-153), the cosmetic speed / lifetime rewrite of emitted particles in
+    handle_decay (:295-342) and the free-particle animation update_particle (:178-210)."""
+    import importlib
+    from collections import deque
+    ns = importlib.import_module("nuclear_sim")
+    pm, dc = R.particles, R.decay_chains
+    out = {"source": "nuclear_sim.py:118-176,178-210,295-347"}
+
+    def fresh():
+        sim = object.__new__(ns.NuclearSimulation)
+        sim.fps_history = deque(maxlen=30)
+        sim.time_scale, sim.time_passed = 1.0, 0
+        sim.camera_pos, sim.camera_target = [400, 400], [400, 400]
+        sim.zoom_level = sim.target_zoom = 15.0
+        sim.zoom_speed = 0.1
+        sim.auto_adjust_substeps, sim.physics_dt_factor = False, 0.8
+        sim.physics_dt, sim.accuracy, sim.max_substeps, sim.substeps_used = 1 / 240, 1, 20, 0
+        sim.nucleus, sim.particles, sim.gpu_available = None, [], False
+        sim.decay_times = deque(maxlen=100)
+        return sim
+
+    plans = []
+    ns.random = ref_loader.DrawFeeder([0.5] * 100000)
+    for auto in (False, True):
+        for ts in (1e-3, 0.5, 1.0, 2.0, 10.0, 60.0, 3600.0, 31557600.0, 3.15576e16):
+            for dt in (1 / 240, 1 / 144, 1 / 60, 1 / 30, 0.1, 0.5):
+                sim = fresh()
+                sim.auto_adjust_substeps, sim.time_scale = auto, ts
+                sim.update_simulation(dt)
+                plans.append(dict(auto=auto, time_scale=hx(ts), dt=hx(dt), num_steps=sim.substeps_used,
+                                  physics_dt=hx(sim.physics_dt), time_passed=hx(float(sim.time_passed))))
+    out["plans"] = plans
+
+    cosmetics = []
+    for ts in (0.5, 1.0, 60.0, 86400.0, 31557600000.0):
+        for sub in (1, 4, 12, 16, 20):
+            for pdt in (1 / 240, 1 / 60, 1 / 1000):
+                for (z, n) in ((92, 146), (6, 8), (84, 134), (43, 56)):
+                    sim = fresh()
+                    sim.time_scale, sim.substeps_used, sim.physics_dt = ts, sub, pdt
+                    random.seed(z)
+                    nuc = pm.Nucleus(z, n, 0.0, 0.0)
+                    nuc.stability = 1.0
+                    nuc.decay_chain, nuc.last_decay_time = [], 0.0
+                    sim.nucleus, sim.time_passed = nuc, 10.0
+                    dc.random = ref_loader.DrawFeeder([0.7, 0.3, 0.4])
+                    ns.random = ref_loader.DrawFeeder([0.5] * 16)
+                    sim.handle_decay()
+                    for p in sim.particles:
+                        cosmetics.append(dict(time_scale=hx(ts), substeps=sub, physics_dt=hx(pdt),
+                                              ptype=p.type.value, vx=hx(p.vx), vy=hx(p.vy),
+                                              lifetime=hx(float(p.lifetime))))
+    dc.random = random
+    out["cosmetics"] = cosmetics
+
+    anim = []
+    for ts in (1.0, 50.0, 1e4):
+        for sub in (1, 4, 20):
+            for ptype in (pm.ParticleType.ALPHA, pm.ParticleType.ELECTRON, pm.ParticleType.GAMMA,
+                          pm.ParticleType.POSITRON, pm.ParticleType.NEUTRON, pm.ParticleType.PROTON):
+                sim = fresh()
+                sim.time_scale, sim.substeps_used = ts, sub
+                p = pm.Particle(1.0, -2.0, ptype, 30.0, -40.0)
+                p.lifetime = 0.05 if ptype != pm.ParticleType.NEUTRON else p.lifetime
+                alive = []
+                for k in range(6):
+                    alive.append(bool(sim.update_particle(p, 1 / 240, 0.004 * (k + 1))))
+                anim.append(dict(time_scale=hx(ts), substeps=sub, ptype=ptype.value, x=hx(p.x),
+                                 y=hx(p.y), age=hx(float(p.age)), alive=alive))
+    out["animation"] = anim
+    ns.random = random
+    with gzip.open(os.path.join(GOLD, "sim_driver.json.gz"), "wt") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("sim driver:", len(plans), "plans,", len(cosmetics), "cosmetic cases,", len(anim), "animation cases")
+
+
 def check_handle_decay_slice():
     """Sanity: the physics slice used above equals the real NuclearSimulation.handle_decay
     (nuclear_sim.py:212-353) in Z, N, particle list, centre and stability."""
@@ -511,7 +590,7 @@ def check_handle_decay_slice():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["data", "kats", "tables", "events", "check", "overlaps", "layouts", "traj"]
+    what = sys.argv[1:] or ["data", "kats", "tables", "events", "check", "overlaps", "driver", "layouts", "traj"]
     if "data" in what:
         gen_nuclide_data()
     if "kats" in what:
@@ -524,6 +603,8 @@ if __name__ == "__main__":
         check_handle_decay_slice()
     if "overlaps" in what:
         gen_resolve_overlaps()
+    if "driver" in what:
+        gen_sim_driver()
     if "layouts" in what:
         gen_layouts()
     if "traj" in what:

@@ -237,3 +237,29 @@ def test_full_size_ensemble_properties():
         ox, oy, _, _, _, _, amb = oracle_step(p0h[k], np.zeros((208, 2), np.float32), isp[k],
                                               ens.dt_phys)
         assert pos_error(p0h[k], p1h[k], ox, oy, amb) <= POS_TOL
+
+
+def test_branch_census_matches_oracle_statistics():
+    """The device-side branch census behind the roofline's FLOP count equals the oracle's
+    BranchStats on the same nuclei (FP32 vs FP64 threshold flips aside)."""
+    from pyqmd_b200.state import NucleusEnsemble, README_ISOTOPES
+    ens = NucleusEnsemble.from_templates(README_ISOTOPES, 45, decay=False)
+    ens.step(3)
+    counts, flops_pair = ens.census()
+    off, cnt = ens.offsets.cpu().numpy(), ens.count.cpu().numpy()
+    pos, isp = ens.pos.cpu().numpy(), ens.is_proton.cpu().numpy()
+    tot = {k: 0 for k in counts}
+    flops = pairs = 0
+    for k in range(ens.n_nuclei):
+        sl = slice(off[k], off[k] + cnt[k])
+        x, y = pos[sl, 0].astype(np.float64), pos[sl, 1].astype(np.float64)
+        r = orc.force_step(x, y, np.zeros(cnt[k]), np.zeros(cnt[k]), isp[sl], 1 / 240,
+                           integrate=False, want_stats=True)
+        st = r["stats"].as_dict()
+        for name in tot:
+            tot[name] += st[name]
+        flops += r["stats"].flops()
+        pairs += cnt[k] * (cnt[k] - 1)
+    for name in tot:
+        assert abs(tot[name] - counts[name]) <= 4 + 1e-4 * tot[name], (name, tot[name], counts[name])
+    assert abs(flops / pairs - flops_pair) < 1e-3

@@ -1,0 +1,87 @@
+"""GPU tests of the headless frame driver (pyqmd_b200.sim.HeadlessSimulation): the caller side of
+the hot path, nuclear_sim.py:118-176 for many nuclei at once."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from pyqmd_b200 import nuclides
+from pyqmd_b200.sim import TIME_SCALE_PRESETS, HeadlessSimulation, substep_plan
+from pyqmd_b200.types import DecayType, ParticleType
+
+pytestmark = pytest.mark.gpu
+
+
+def test_set_dt_decay_recomputes_probabilities_bit_exact():
+    sim = HeadlessSimulation(isotopes=((6, 8), (92, 146), (82, 126), (84, 134)), n_nuclei=64)
+    ens = sim.ensemble
+    for dt in (1 / 240, 180825048000.0 * 1e-3, 1.409993568e17 * 0.1, 3.0):
+        ens.set_dt_decay(dt)
+        T = ens.half_life.cpu().numpy()
+        p = ens.p_decay.cpu().numpy()
+        want = np.array([nuclides.decay_probability(float(t), dt) for t in T])
+        assert np.array_equal(p, want)
+        tab = ens.table.cpu().numpy()
+        assert np.array_equal(tab, nuclides.build_device_table(dt).view(np.uint8))
+
+
+def test_frames_decay_counts_and_free_particles():
+    n = 2048
+    sim = HeadlessSimulation((6, 8), n_nuclei=n, seed=11)
+    T = nuclides.get_half_life(6, 8)
+    # pick the time scale so that a frame of 1/60 s covers T/50: 20 sub-steps of T/1000 (linear branch)
+    sim.time_scale = T / 50 * 60
+    frames = 12
+    for _ in range(frames):
+        sim.update_simulation(1 / 60)
+    num_steps, eff, step_time, _ = substep_plan(1 / 60, sim.time_scale)
+    assert sim.substeps_used == num_steps == 20 and eff == 1 / 240
+    assert sim.ensemble.dt_phys == eff and sim.ensemble.dt_decay == step_time
+    assert sim.time_passed == pytest.approx(frames / 60 * sim.time_scale)
+    # C-14 -> N-14 (stable): every nucleus decays at most once, by beta-minus
+    counts = sim.decay_counts
+    total = sum(counts.values())
+    assert counts["BETA_MINUS"] == total > 0
+    zn = sim.ensemble.zn.cpu().numpy()
+    assert int((zn == nuclides.zn_pack(7, 7)).sum()) == total
+    p = nuclides.decay_probability(T, step_time)
+    k = frames * num_steps
+    expect = n * (1 - (1 - p) ** k)
+    sigma = math.sqrt(n * (1 - p) ** k * (1 - (1 - p) ** k))
+    assert abs(total - expect) < 5 * sigma + 1, (total, expect, sigma)
+    # emitted electrons: renormalised to 50 (nuclear_sim.py:305-307) and not yet expired
+    f = sim.free_particles
+    assert len(f["x"]) <= total
+    if len(f["x"]):
+        assert set(np.unique(f["type"]).tolist()) <= {ParticleType.ELECTRON.value}
+        assert np.allclose(np.hypot(f["vx"], f["vy"]), 50.0, rtol=0, atol=1e-9)
+        assert (f["age"] < f["lifetime"]).all()
+    # the ensemble counters and the event log agree
+    ev = sim.ensemble.events()
+    assert len(ev) == total and (ev["mode"] == DecayType.BETA_MINUS.value).all()
+
+
+def test_alpha_chain_with_projection_keeps_nuclei_physical():
+    sim = HeadlessSimulation((92, 146), n_nuclei=96, seed=5,
+                             time_scale=TIME_SCALE_PRESETS["billion"] * 2000)
+    for _ in range(6):
+        sim.update_simulation(1 / 60)
+    ens = sim.ensemble
+    cnt = ens.count.cpu().numpy()
+    zn = ens.zn.cpu().numpy()
+    assert sim.decay_counts["ALPHA"] > 0
+    assert cnt.min() >= 238 - 4 * 8 and cnt.max() <= 238
+    assert torch.isfinite(ens.pos).all()
+    # render bridge: a Nucleus whose particle list mirrors the device state
+    k = int(np.argmin(cnt))
+    nuc = sim.nucleus_view(k)
+    assert len(nuc.particles) == cnt[k]
+    assert (nuc.protons, nuc.neutrons) == nuclides.zn_unpack(int(zn[k]))
+    n_p = sum(1 for q in nuc.particles if q.type == ParticleType.PROTON)
+    # alpha removes 2 p + 2 n, beta-minus turns n -> p: the particle list follows (Z, N) on this chain
+    assert n_p == nuc.protons and len(nuc.particles) - n_p == nuc.neutrons
+    xs = np.array([q.x for q in nuc.particles]); ys = np.array([q.y for q in nuc.particles])
+    assert abs(xs.mean() - 400.0) < 30 and abs(ys.mean() - 400.0) < 30      # origin (400, 400), :93
+    ext = np.hypot(xs - xs.mean(), ys - ys.mean()).max()
+    assert 10.0 < ext < 200.0
