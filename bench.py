@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--nuclei", type=int, default=0, help="override nuclei per GPU (ensemble/mixed)")
     ap.add_argument("--cloud-n", type=int, default=N_CLOUD)
+    ap.add_argument("--cloud-scheme", default="symmetric", choices=["symmetric", "ordered"],
+                    help="symmetric: every unordered pair once + integer force reduce-scatter; "
+                         "ordered: i-block rows x all j, position all-gather only")
     ap.add_argument("--substeps", type=int, default=1, help="sub-steps fused per step call")
     return ap.parse_args()
 
@@ -416,7 +419,7 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
     from pyqmd_b200.state import NucleonCloud
     n = args.cloud_n
     pos, isp = make_cloud(n)
-    cloud = NucleonCloud(pos, isp, device=dev, rank=rank, world=world)
+    cloud = NucleonCloud(pos, isp, device=dev, rank=rank, world=world, scheme=args.cloud_scheme)
     sec = timed_steps(lambda: cloud.step(1), K, W, dist, torch, sampler)
     pairs = float(n) * (n - 1)
     f_pp = (float(isp.sum()) / n) ** 2
@@ -428,7 +431,10 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
                                f"i-block sharded x{world}" + (" + NCCL position all-gather" if world > 1 else ""),
                    "l2_policy": "per-step working set (positions 8N B) is L2 resident by design; "
                                 "compute bound", "dt_phys": 1 / 240,
-                   "parallelism": f"i-block x{world}"},
+                   "scheme": args.cloud_scheme,
+                   "parallelism": (f"i-block rows dealt x{world}, integer force reduce-scatter + position "
+                                   f"all-gather" if args.cloud_scheme == "symmetric" and world > 1 else
+                                   f"i-block x{world}")},
         "roofline": {"bound": "fp32", "achieved": mine * flops_pair / 1e12, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak, "traffic": None,
                      "kernel": "cloud_force_kernel", "flops_per_pair": flops_pair,

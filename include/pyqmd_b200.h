@@ -85,7 +85,7 @@ int pyqmd_update_particles_f64(double *x, double *y, double *vx, double *vy,
 /* ---------------------------------------------------------------------------------------- */
 /* (B) one large nucleon cloud resident on the device (BASELINE config 4)                    */
 
-/* bytes of scratch pyqmd_cloud_step needs for n nucleons */
+/* bytes of scratch the cloud entry points need for n nucleons */
 int64_t pyqmd_cloud_workspace_bytes(int64_t n);
 
 /*
@@ -103,6 +103,29 @@ int64_t pyqmd_cloud_workspace_bytes(int64_t n);
 int pyqmd_cloud_step(const float *pos_in, float *pos_out, float *vel, float *force,
                      const uint8_t *is_proton, int64_t n, int64_t i0, int64_t i1, float strong,
                      float coulomb, float pauli, float dt, void *workspace, void *stream);
+
+/*
+ * The same step split in two, with every unordered pair evaluated once (the law is symmetric, so
+ * the force on j is the negated force on i, nuclear_forces.py:253-298) -- about twice as fast as
+ * the ordered i-block scheme of pyqmd_cloud_step on any number of GPUs:
+ *
+ *   pyqmd_cloud_pair_forces  adds this part's share (`part` of `n_parts`: i-block rows of 1024
+ *       nucleons dealt boustrophedon-wise, each with the j tiles at and after its diagonal) of the
+ *       pair forces on ALL n nucleons into force_acc, int64[n][2] fixed point with scale
+ *       2^pyqmd_cloud_force_scale_log2(n).  Integer accumulation is associative: the sum over
+ *       parts (an integer reduce-scatter between GPUs) is bit-identical for any n_parts.
+ *       force_acc must be zero before the first part is added.
+ *   pyqmd_cloud_integrate    consumes and CLEARS the accumulators of [i0, i1) (force_acc_i0 points
+ *       at the entry of nucleon i0): containment (:301-309) + damped Euler (:312-323).  Uses the
+ *       centre of mass left in `workspace` by pyqmd_cloud_pair_forces.
+ */
+int32_t pyqmd_cloud_force_scale_log2(int64_t n);
+int pyqmd_cloud_pair_forces(const float *pos, const uint8_t *is_proton, int64_t n, int32_t part,
+                            int32_t n_parts, float strong, float coulomb, float pauli,
+                            long long *force_acc, void *workspace, void *stream);
+int pyqmd_cloud_integrate(const float *pos_in, float *pos_out, float *vel, float *force, int64_t n,
+                          int64_t i0, int64_t i1, float dt, long long *force_acc_i0,
+                          void *workspace, void *stream);
 
 /* 64-bit sort keys: bit 63 = neutron, low bits = 2-D Morton code of the position inside
  * [xmin, xmin+extent) x [ymin, ymin+extent).  Sorting by key gives the layout above. */

@@ -16,61 +16,9 @@
 //    (pyqmd_cloud_sort_keys) > 99.9 % of tile visits are far;
 //  * Jacobi update: reads pos_in, writes pos_out (the reference's OpenCL kernel updates in
 //    place and races; the CPU path, which is the parity target, is Jacobi).
-#include "common.cuh"
-#include "pair_law.cuh"
+#include "cloud.cuh"
 
 namespace pyqmd {
-
-constexpr int kTile = 256;      // j-tile size == tile-statistics granularity
-constexpr int kThreads = 256;   // threads per block of the force kernel
-constexpr int kIPT = 4;         // i-nucleons per thread
-constexpr int kIBlock = kThreads * kIPT;
-
-enum : int { kTileAllProton = 1, kTileAllNeutron = 2 };
-
-struct CloudWorkspace {
-    double* centre;   // [2] float64 centre of mass
-    float4* bbox;     // [n_tiles] xmin, ymin, xmax, ymax
-    double2* sums;    // [n_tiles] partial coordinate sums
-    int* flags;       // [n_tiles] kTileAll*
-    double2* partial; // [n_seg][i1 - i0] per-segment partial forces
-};
-
-constexpr int64_t kTargetUnits = 8192;   // ~28 work units per resident-block slot (148 SMs x 2)
-constexpr int kMaxSeg = 64;
-
-// number of j segments for an i-range of n_i nucleons of an n-nucleon cloud
-__host__ inline int segments_for(int64_t n, int64_t n_i)
-{
-    const int64_t iblocks = (n_i + kIBlock - 1) / kIBlock;
-    const int64_t tiles = (n + kTile - 1) / kTile;
-    int64_t s = (kTargetUnits + iblocks - 1) / (iblocks > 0 ? iblocks : 1);
-    if (s > kMaxSeg) s = kMaxSeg;
-    if (s > tiles) s = tiles;
-    if (s < 1) s = 1;
-    return (int)s;
-}
-
-__host__ __device__ inline int64_t n_tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
-
-static int64_t partial_entries(int64_t n)
-{
-    // worst case over all i-ranges [i0, i1) of an n-nucleon cloud of n_seg * (i1 - i0)
-    return n + (kTargetUnits + kMaxSeg) * (int64_t)kIBlock;
-}
-
-static CloudWorkspace carve(void* ws, int64_t n)
-{
-    const int64_t nt = n_tiles_of(n);
-    unsigned char* p = reinterpret_cast<unsigned char*>(ws);
-    CloudWorkspace w;
-    w.centre = reinterpret_cast<double*>(p);            p += 32;
-    w.bbox = reinterpret_cast<float4*>(p);              p += sizeof(float4) * nt;
-    w.sums = reinterpret_cast<double2*>(p);             p += sizeof(double2) * nt;
-    w.flags = reinterpret_cast<int*>(p);              p += (sizeof(int) * nt + 255) / 256 * 256;
-    w.partial = reinterpret_cast<double2*>(p);
-    return w;
-}
 
 // ---- pass 1: per-tile bounding box, type flag, coordinate sums ---------------------------------
 __global__ void __launch_bounds__(kTile) cloud_tile_stats(const float2* __restrict__ pos,
@@ -148,58 +96,17 @@ __global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_
 // ---- pass 3: partial forces of one work unit = (i-block, j-segment) --------------------------------
 //
 // Packed FP32 (Blackwell add/mul/fma.f32x2 -> FADD2/FMUL2/FFMA2): one instruction works on two
-// pairs, so the 14 FMA-pipe operations of a far pair cost 7 issue slots instead of 14 and the
-// kernel moves from issue-bound (ncu r01a: 82 % issue, 18 instr/pair) towards the MUFU limit of
-// 2 special-function ops per pair.
-struct FarConsts {
-    f32x2 kexp, logA, c3, c2, c1, one, e2, ne, negC;
-};
+// pairs, so the FMA-pipe operations of a far pair cost half the issue slots and the kernel moves
+// from issue-bound (ncu r01a: 82 % issue, 18 instr/pair) to pipe-bound.  ncu r01e (14 FMA-pipe ops
+// + 2 special-function ops per pair): XU pipe 84 %, FMA pipe ~80 % busy -- both near saturation,
+// so this version (a) trims the FMA work to 12 ops per pair and (b) moves a fixed share of the
+// 2^x evaluations from the XU pipe to an FMA-pipe polynomial to balance the two pipes.
+// NPOLY of the 8 packed evaluations per (4 i x 4 j) inner iteration take the polynomial 2^x.
+#ifndef PYQMD_CLOUD_NPOLY
+#define PYQMD_CLOUD_NPOLY 0
+#endif
 
-__device__ __forceinline__ FarConsts make_far_consts(const LawParams& L)
-{
-    FarConsts c;
-    const float k = -1.8f * kLog2e / 7.0f;
-    c.kexp = pk(k, k);
-    c.logA = pk(L.log2TailK, L.log2TailK);
-    c.c3 = pk(-kEps * kEps * kEps, -kEps * kEps * kEps);
-    c.c2 = pk(kEps * kEps, kEps * kEps);
-    c.c1 = pk(-kEps, -kEps);
-    c.one = pk(1.0f, 1.0f);
-    c.e2 = pk(kEps * kEps, kEps * kEps);
-    c.ne = pk(-kEps, -kEps);
-    c.negC = pk(-L.C, -L.C);
-    return c;
-}
-
-// Two far pairs (one i, two j) in packed form; same arithmetic as pair_far_impl<MODE,false>.
-template <int MODE>
-__device__ __forceinline__ void far_pair2(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
-                                          const FarConsts& c, f32x2& fx, f32x2& fy)
-{
-    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
-    const f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
-    float a0, a1;
-    upk(d2, a0, a1);
-    const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
-    const f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
-    upk(arg, a0, a1);
-    const f32x2 e = pk(mufu_ex2(a0), mufu_ex2(a1));
-    f32x2 h = fma2(r, c.c3, c.c2);
-    h = fma2(r, h, c.c1);
-    h = fma2(r, h, c.one);
-    const f32x2 r2 = mul2(r, r);
-    f32x2 s = mul2(e, mul2(h, r2));
-    if (MODE != 0) {
-        f32x2 g = fma2(r2, c.e2, c.ne);
-        g = fma2(r2, g, c.one);
-        const f32x2 q = (MODE == 1) ? c.negC : cq;          // cq already carries the minus sign
-        s = fma2(mul2(q, r), mul2(g, r2), s);
-    }
-    fx = fma2(dx, s, fx);
-    fy = fma2(dy, s, fy);
-}
-
-template <int MODE>
+template <int MODE, int NPOLY>
 __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
                                                 const float* __restrict__ sy,
                                                 const float* __restrict__ st, int jmax,
@@ -228,10 +135,21 @@ __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
         if (MODE == 2) T = t4[jq];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            far_pair2<MODE>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull, c,
-                            ax[k], ay[k]);
-            far_pair2<MODE>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull, c,
-                            ax[k], ay[k]);
+            // the polynomial evaluations are spread over the iteration (k = 0, 2, 1, 3 first halves)
+            constexpr int order[4] = {0, 2, 1, 3};
+            const bool pa = order[k] < NPOLY, pb = order[k] + 4 < NPOLY;
+            if (pa)
+                far_pair2<MODE, true>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull,
+                                      c, ax[k], ay[k]);
+            else
+                far_pair2<MODE, false>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull,
+                                       c, ax[k], ay[k]);
+            if (pb)
+                far_pair2<MODE, true>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull,
+                                      c, ax[k], ay[k]);
+            else
+                far_pair2<MODE, false>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull,
+                                       c, ax[k], ay[k]);
         }
     }
 #pragma unroll
@@ -249,6 +167,63 @@ __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
             fx[k] = fmaf(dx, sc, fx[k]);
             fy[k] = fmaf(dy, sc, fy[k]);
         }
+    }
+}
+
+// Scalar twin of far_pair2 (same arithmetic, one pair per instruction), kept for A/B measurements of
+// packed vs scalar issue cost (PYQMD_CLOUD_SCALAR=1).
+template <int MODE>
+__device__ __forceinline__ void far_pair1(float xj, float yj, float xi, float yi, float cq,
+                                          const LawParams& L, float& fx, float& fy)
+{
+    const float dx = xj - xi, dy = yj - yi;
+    const float d2 = fmaf(dy, dy, dx * dx);
+    const float r = mufu_rsqrt(d2);
+    float arg = fmaf(d2 * r, -1.8f * kLog2e / 7.0f, L.log2TailK);
+    arg = fmaf(r, fmaf(r, kL2, kL1), arg);
+    const float e = mufu_ex2(arg);
+    const float r2 = r * r;
+    float s;
+    if (MODE == 0) {
+        s = e * r2;
+    } else {
+        const float g = fmaf(r2, fmaf(r2, kG2, kG1), 1.0f);
+        const float q = (MODE == 1) ? -L.C : cq;
+        s = r2 * fmaf(q * r, g, e);
+    }
+    fx = fmaf(dx, s, fx);
+    fy = fmaf(dy, s, fy);
+}
+
+template <int MODE>
+__device__ __forceinline__ void far_tile_scalar(const float* __restrict__ sx,
+                                                const float* __restrict__ sy,
+                                                const float* __restrict__ st, int jmax,
+                                                const float (&xi)[kIPT], const float (&yi)[kIPT],
+                                                const float (&qi)[kIPT], float (&fx)[kIPT],
+                                                float (&fy)[kIPT], const LawParams& L)
+{
+    const int quads = jmax >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(sx);
+    const float4* y4 = reinterpret_cast<const float4*>(sy);
+    const float4* t4 = reinterpret_cast<const float4*>(st);
+#pragma unroll 1
+    for (int jq = 0; jq < quads; ++jq) {
+        const float4 X = x4[jq], Y = y4[jq];
+        float4 T = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 2) T = t4[jq];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            far_pair1<MODE>(X.x, Y.x, xi[k], yi[k], -qi[k] * T.x, L, fx[k], fy[k]);
+            far_pair1<MODE>(X.y, Y.y, xi[k], yi[k], -qi[k] * T.y, L, fx[k], fy[k]);
+            far_pair1<MODE>(X.z, Y.z, xi[k], yi[k], -qi[k] * T.z, L, fx[k], fy[k]);
+            far_pair1<MODE>(X.w, Y.w, xi[k], yi[k], -qi[k] * T.w, L, fx[k], fy[k]);
+        }
+    }
+    for (int j = quads << 2; j < jmax; ++j) {
+        const float ox = sx[j], oy = sy[j], tj = st[j];
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) far_pair1<MODE>(ox, oy, xi[k], yi[k], -qi[k] * tj, L, fx[k], fy[k]);
     }
 }
 
@@ -297,7 +272,7 @@ __device__ __forceinline__ void near_tile(const float* __restrict__ sx, const fl
 // float64 partial sums to partial[s][i - i0].  Splitting the j range keeps >= ~10 work units
 // per resident-block slot whatever N and the number of ranks are (wave quantisation was
 // costing 18 % at N = 1M on one GPU and > 50 % on eight).
-template <bool CLAMP>
+template <bool CLAMP, int NPOLY>
 __global__ void __launch_bounds__(kThreads, 2)
 cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict__ isp, int64_t n,
                    int64_t i0, int64_t i1, CloudWorkspace w, LawParams L, int far_enabled,
@@ -394,9 +369,16 @@ cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict_
                 else if (mode == 1) far_tile_clamped<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
                 else far_tile_clamped<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
             } else {
-                if (mode == 0) far_tile_packed<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                else if (mode == 1) far_tile_packed<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                else far_tile_packed<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                if (NPOLY < 0) {
+                    if (mode == 0) far_tile_scalar<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                    else if (mode == 1) far_tile_scalar<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                    else far_tile_scalar<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                } else {
+                    constexpr int NP = NPOLY < 0 ? 0 : NPOLY;
+                    if (mode == 0) far_tile_packed<0, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                    else if (mode == 1) far_tile_packed<1, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                    else far_tile_packed<2, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                }
             }
         } else {
             near_tile(sx, sy, st, jmax, xi, yi, ti, fx, fy, L);
@@ -472,6 +454,18 @@ __global__ void cloud_sort_keys_kernel(const float2* __restrict__ pos, const uin
     keys[i] = key;
 }
 
+// tile statistics + centre of mass, shared with the symmetric scheme (cloud_sym.cu)
+int cloud_prepass(const float* pos, const uint8_t* is_proton, int64_t n, const CloudWorkspace& w,
+                  cudaStream_t st)
+{
+    const int64_t nt = n_tiles_of(n);
+    cloud_tile_stats<<<(unsigned)nt, kTile, 0, st>>>(reinterpret_cast<const float2*>(pos), is_proton,
+                                                     n, w);
+    cloud_centre<<<1, 256, 0, st>>>(w, nt, n);
+    PYQMD_CUDA_CHECK(cudaGetLastError());
+    return PYQMD_OK;
+}
+
 }  // namespace pyqmd
 
 using namespace pyqmd;
@@ -498,9 +492,10 @@ extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel,
     const int64_t nt = n_tiles_of(n);
     PYQMD_REQUIRE(nt <= 2147483647LL, "cloud too large");
     const LawParams L = make_law_params(strong, coulomb, pauli);
-    cloud_tile_stats<<<(unsigned)nt, kTile, 0, st>>>(reinterpret_cast<const float2*>(pos_in),
-                                                     is_proton, n, w);
-    cloud_centre<<<1, 256, 0, st>>>(w, nt, n);
+    {
+        const int rc = cloud_prepass(pos_in, is_proton, n, w, st);
+        if (rc != PYQMD_OK) return rc;
+    }
     const int64_t blocks = (i1 - i0 + kIBlock - 1) / kIBlock;
     const int far_enabled = strong > 0.f ? 1 : 0;
     const int n_seg = segments_for(n, i1 - i0);
@@ -508,12 +503,25 @@ extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel,
     PYQMD_REQUIRE((int64_t)n_seg * (i1 - i0) <= partial_entries(n), "workspace too small");
     const dim3 grid((unsigned)blocks, (unsigned)n_seg);
     const float2* pin = reinterpret_cast<const float2*>(pos_in);
-    if (L.far_needs_clamp)
-        cloud_force_kernel<true><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
-                                                            far_enabled, tiles_per_seg);
-    else
-        cloud_force_kernel<false><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
-                                                             far_enabled, tiles_per_seg);
+    // tuning knob (read once): share of polynomial 2^x evaluations, 0..4 of 8
+    static int npoly = -1;
+    if (npoly < 0) {
+        const char* env = getenv("PYQMD_CLOUD_NPOLY");
+        npoly = env ? atoi(env) : PYQMD_CLOUD_NPOLY;
+        if (npoly < 0 || npoly > 4) npoly = PYQMD_CLOUD_NPOLY;
+        if (getenv("PYQMD_CLOUD_SCALAR")) npoly = 9;
+    }
+#define PYQMD_LAUNCH_FORCE(CL, NP)                                                                  \
+    cloud_force_kernel<CL, NP><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,          \
+                                                          far_enabled, tiles_per_seg)
+    if (L.far_needs_clamp) PYQMD_LAUNCH_FORCE(true, 0);
+    else if (npoly == 0) PYQMD_LAUNCH_FORCE(false, 0);
+    else if (npoly == 1) PYQMD_LAUNCH_FORCE(false, 1);
+    else if (npoly == 2) PYQMD_LAUNCH_FORCE(false, 2);
+    else if (npoly == 3) PYQMD_LAUNCH_FORCE(false, 3);
+    else if (npoly == 9) PYQMD_LAUNCH_FORCE(false, -1);
+    else PYQMD_LAUNCH_FORCE(false, 4);
+#undef PYQMD_LAUNCH_FORCE
     cloud_integrate_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, st>>>(
         pin, reinterpret_cast<float2*>(pos_out), reinterpret_cast<float2*>(vel),
         reinterpret_cast<float2*>(force), n, i0, i1, w, n_seg, dt);

@@ -28,6 +28,32 @@ def cloud_chunk(n: int, world: int) -> int:
     return (n + world - 1) // world
 
 
+CLOUD_ROW = 1024     # nucleons per i-block row of the symmetric cloud scheme (csrc/cloud.cuh kIBlock)
+
+
+def sym_rows_of(part: int, n_parts: int, n: int):
+    """i-block rows of the symmetric cloud scheme that ``part`` evaluates (csrc/cloud_sym.cu): rows
+    are dealt boustrophedon-wise -- row g*n_parts + (part if g even else n_parts-1-part) -- so that
+    the triangular work (row b meets the tiles at and after its diagonal) is balanced."""
+    nb = (n + CLOUD_ROW - 1) // CLOUD_ROW
+    rows = []
+    g = 0
+    while True:
+        b = g * n_parts + (n_parts - 1 - part if g & 1 else part)
+        if g * n_parts >= nb:
+            break
+        if b < nb:
+            rows.append(b)
+        g += 1
+    return rows
+
+
+def sym_row_work(b: int, n: int) -> int:
+    """j-tiles (256 nucleons) row ``b`` visits: its 4 diagonal tiles and every tile after them."""
+    nt = (n + 255) // 256
+    return max(nt - 4 * b, 0)
+
+
 def allgather_positions(replica: torch.Tensor, rank: int, world: int, chunk: int, group=None):
     """In-place all-gather of the rows each rank owns in its [chunk * world, 2] replica."""
     if world == 1:

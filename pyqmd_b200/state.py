@@ -367,13 +367,22 @@ class HostEnsembleRunner:
 
 # =================================================================================================
 class NucleonCloud:
-    """One N-nucleon system; rank ``rank`` of ``world`` owns the i-block [i0, i1) and every rank
-    holds a full replica of the positions, refreshed by an all-gather after each step."""
+    """One N-nucleon system on ``world`` GPUs.  Every rank holds a full replica of the positions and
+    owns the i-block [i0, i1) for the integration; new positions are all-gathered after each step.
+
+    scheme="symmetric" (default): every unordered pair is evaluated once (the law is symmetric);
+        i-block rows are dealt to the ranks, each rank adds its share of the forces on ALL nucleons
+        into int64 fixed-point accumulators, an integer reduce-scatter delivers every rank the
+        exact, order-independent totals of its own block.
+    scheme="ordered": rank r evaluates the ordered pairs (i, j) for its own i only (the
+        decomposition BASELINE.json names: i-block + position all-gather, no force exchange).
+    """
 
     def __init__(self, pos, is_proton, vel=None, *, device="cuda", dt=DEFAULT_DT,
                  strengths=DEFAULT_STRENGTHS, rank=0, world=1, group=None, sort=True,
-                 keep_force=False):
+                 keep_force=False, scheme="symmetric"):
         _lib.require_cuda()
+        assert scheme in ("symmetric", "ordered")
         dev = self.device = torch.device(device)
         pos = torch.as_tensor(pos, dtype=torch.float32).reshape(-1, 2).to(dev)
         isp = torch.as_tensor(is_proton, dtype=torch.uint8).to(dev)
@@ -382,6 +391,7 @@ class NucleonCloud:
         self.n = int(pos.shape[0])
         self.dt, self.strengths = float(dt), tuple(float(s) for s in strengths)
         self.rank, self.world, self.group = int(rank), int(world), group
+        self.scheme = scheme
         self.chunk = cloud_chunk(self.n, self.world)
         self.i0, self.i1 = shard_range(self.n, self.rank, self.world)
         self.perm = None
@@ -397,6 +407,13 @@ class NucleonCloud:
         self.force = torch.zeros(self.n, 2, device=dev, dtype=torch.float32) if keep_force else None
         ws = int(_lib.lib().pyqmd_cloud_workspace_bytes(self.n))
         self.workspace = torch.zeros(max(ws, 64), dtype=torch.uint8, device=dev)
+        # fixed-point force accumulators of the symmetric scheme (kept zero between steps)
+        self.acc = self.acc_mine = None
+        if scheme == "symmetric":
+            self.acc = torch.zeros(padded, 2, device=dev, dtype=torch.int64)
+            self.acc_mine = (torch.zeros(self.chunk, 2, device=dev, dtype=torch.int64)
+                             if self.world > 1 else self.acc)
+        self.force_scale_log2 = int(_lib.lib().pyqmd_cloud_force_scale_log2(max(self.n, 1)))
         self.steps_done = 0
 
     def _sort_perm(self, pos, isp):
@@ -412,10 +429,30 @@ class NucleonCloud:
         lib = _lib.lib()
         S, Cc, P = self.strengths
         for _ in range(n_steps):
-            _lib.check(lib.pyqmd_cloud_step(
-                self.pos.data_ptr(), self.pos_next.data_ptr(), self.vel.data_ptr(),
-                _lib.ptr(self.force), self.is_proton.data_ptr(), self.n, self.i0, self.i1, S, Cc,
-                P, self.dt, self.workspace.data_ptr(), _lib.current_stream()), "pyqmd_cloud_step")
+            stream = _lib.current_stream()
+            if self.acc is None:
+                # ordered i-block scheme: forces on [i0, i1) from all j, no force exchange
+                _lib.check(lib.pyqmd_cloud_step(
+                    self.pos.data_ptr(), self.pos_next.data_ptr(), self.vel.data_ptr(),
+                    _lib.ptr(self.force), self.is_proton.data_ptr(), self.n, self.i0, self.i1, S, Cc,
+                    P, self.dt, self.workspace.data_ptr(), stream), "pyqmd_cloud_step")
+            else:
+                import torch.distributed as dist
+                _lib.check(lib.pyqmd_cloud_pair_forces(
+                    self.pos.data_ptr(), self.is_proton.data_ptr(), self.n, self.rank, self.world,
+                    S, Cc, P, self.acc.data_ptr(), self.workspace.data_ptr(), stream),
+                    "pyqmd_cloud_pair_forces")
+                if self.world > 1:
+                    dist.reduce_scatter_tensor(self.acc_mine, self.acc, op=dist.ReduceOp.SUM,
+                                               group=self.group)
+                    self.acc.zero_()
+                if self.i1 > self.i0:
+                    _lib.check(lib.pyqmd_cloud_integrate(
+                        self.pos.data_ptr(), self.pos_next.data_ptr(), self.vel.data_ptr(),
+                        _lib.ptr(self.force), self.n, self.i0, self.i1, self.dt,
+                        self.acc_mine.data_ptr() + (16 * self.i0 if self.world == 1 else 0),
+                        self.workspace.data_ptr(), _lib.current_stream()),
+                        "pyqmd_cloud_integrate")
             allgather_positions(self.pos_next, self.rank, self.world, self.chunk, self.group)
             self.pos, self.pos_next = self.pos_next, self.pos
             self.steps_done += 1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Profiling pass on the GPU box (run through gpurun):  bash scripts_profile.sh <tag>
+# Profiling pass on the GPU box (run through gpurun):  bash scripts/profile.sh <tag>
 # 1. launch list of the default bench command (share of each kernel in the step)
 # 2. one full ncu capture of each hot kernel
 TAG=${1:-r01}

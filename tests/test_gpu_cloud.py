@@ -1,5 +1,6 @@
 """GPU parity of the single-cloud path (BASELINE config 4) against the oracle, through
-pyqmd_cloud_step / pyqmd_cloud_sort_keys."""
+pyqmd_cloud_step (ordered i-block scheme), pyqmd_cloud_pair_forces + pyqmd_cloud_integrate
+(symmetric scheme: every unordered pair once) and pyqmd_cloud_sort_keys."""
 import numpy as np
 import pytest
 import torch
@@ -48,12 +49,16 @@ def rel_l2(a, b, mask=None):
     return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
 
 
+SCHEMES = ["symmetric", "ordered"]
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("sort", [True, False])
-def test_subcloud_4096_forces_and_step(sort):
+def test_subcloud_4096_forces_and_step(sort, scheme):
     from pyqmd_b200.state import NucleonCloud
     n = 4096
     pos, isp = make_cloud(n)
-    cloud = NucleonCloud(pos, isp, sort=sort, keep_force=True)
+    cloud = NucleonCloud(pos, isp, sort=sort, keep_force=True, scheme=scheme)
     cloud.step(1)
     F = cloud.forces().cpu().numpy().astype(np.float64)
     fx, fy = oracle_forces(pos, isp, 0, n)
@@ -71,12 +76,13 @@ def test_subcloud_4096_forces_and_step(sort):
     assert rel_l2(v, 0.85 * Fo * dt, amb) <= 2e-5
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("n", [1, 2, 31, 255, 256, 257, 1023, 1024, 1025, 3000])
-def test_ragged_sizes(n):
+def test_ragged_sizes(n, scheme):
     """Tile (256) and i-block (1024) boundaries, partial last tile, single nucleon."""
     from pyqmd_b200.state import NucleonCloud
     pos, isp = make_cloud(n, seed=n)
-    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud = NucleonCloud(pos, isp, keep_force=True, scheme=scheme)
     cloud.step(1)
     F = cloud.forces().cpu().numpy().astype(np.float64)
     fx, fy = oracle_forces(pos, isp, 0, n)
@@ -88,13 +94,14 @@ def test_ragged_sizes(n):
         assert np.abs(F[~amb]).max() == 0.0
 
 
-def test_dense_cloud_all_branches():
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_dense_cloud_all_branches(scheme):
     """A compressed cloud (mean spacing ~2) exercises hard core, core, attractive, Pauli and
     the clamp in the tiled kernel's near path."""
     from pyqmd_b200.state import NucleonCloud
     n = 2000
     pos, isp = make_cloud(n, seed=7, density=1 / 4)
-    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud = NucleonCloud(pos, isp, keep_force=True, scheme=scheme)
     cloud.step(1)
     F = cloud.forces().cpu().numpy().astype(np.float64)
     fx, fy = oracle_forces(pos, isp, 0, n)
@@ -102,12 +109,13 @@ def test_dense_cloud_all_branches():
     assert rel_l2(F, np.stack([fx, fy], 1), amb) <= FORCE_TOL
 
 
-def test_clamped_far_path_with_large_strengths():
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_clamped_far_path_with_large_strengths(scheme):
     from pyqmd_b200.state import NucleonCloud
     n = 3000
     pos, isp = make_cloud(n, seed=9)
     st = (20000.0, 3000.0, 35.0)          # tail + Coulomb can hit the +-12 cap beyond d = 9
-    cloud = NucleonCloud(pos, isp, keep_force=True, strengths=st)
+    cloud = NucleonCloud(pos, isp, keep_force=True, strengths=st, scheme=scheme)
     cloud.step(1)
     F = cloud.forces().cpu().numpy().astype(np.float64)
     fx, fy = oracle_forces(pos, isp, 0, n, strengths=st)
@@ -122,10 +130,10 @@ def test_i_block_sharding_is_bit_identical():
     from pyqmd_b200.state import NucleonCloud
     n = 5000
     pos, isp = make_cloud(n, seed=3)
-    full = NucleonCloud(pos, isp)
+    full = NucleonCloud(pos, isp, scheme="ordered")
     full.step(1)
-    a = NucleonCloud(pos, isp, rank=0, world=1)
-    b = NucleonCloud(pos, isp, rank=0, world=1)
+    a = NucleonCloud(pos, isp, rank=0, world=1, scheme="ordered")
+    b = NucleonCloud(pos, isp, rank=0, world=1, scheme="ordered")
     # emulate world = 2 without a process group: restrict the i-range by hand
     h = (n + 1) // 2
     a.i0, a.i1 = 0, h
@@ -135,12 +143,53 @@ def test_i_block_sharding_is_bit_identical():
     assert torch.equal(merged, full.pos[:n])
 
 
-def test_large_cloud_sampled_against_oracle():
+def test_symmetric_parts_sum_bit_identically():
+    """The fixed-point accumulators do not depend on how the rows are dealt to parts (what makes the
+    multi-GPU reduce-scatter exact): 1 part == 3 parts == 8 parts, bit for bit; and the symmetric
+    and ordered schemes agree to FP32 rounding."""
+    import ctypes as C
+    from pyqmd_b200 import _lib
+    from pyqmd_b200.state import NucleonCloud
+    n = 20_000
+    pos, isp = make_cloud(n, seed=5)
+    cloud = NucleonCloud(pos, isp, keep_force=True)
+    lib = _lib.lib()
+    accs = []
+    for parts in (1, 3, 8):
+        acc = torch.zeros(n, 2, dtype=torch.int64, device="cuda")
+        for part in range(parts):
+            _lib.check(lib.pyqmd_cloud_pair_forces(
+                cloud.pos.data_ptr(), cloud.is_proton.data_ptr(), n, part, parts, 150.0, 30.0, 35.0,
+                acc.data_ptr(), cloud.workspace.data_ptr(), _lib.current_stream()), "pair_forces")
+        torch.cuda.synchronize()
+        accs.append(acc)
+    assert torch.equal(accs[0], accs[1]) and torch.equal(accs[0], accs[2])
+    assert int(accs[0].abs().max()) > 0
+    # Newton's third law: action and reaction are rounded separately (FP32 partial sums), so the pair
+    # forces cancel over the cloud to FP32 rounding of the summed magnitudes
+    assert accs[0].sum(0).abs().max().item() <= 1e-6 * accs[0].abs().sum().item()
+    scale = 2.0 ** cloud.force_scale_log2
+    F_sym = (accs[0].double() / scale).cpu().numpy()
+    ordered = NucleonCloud(pos, isp, keep_force=True, scheme="ordered")
+    ordered.step(1)
+    cloud.step(1)
+    Fo, Fs = ordered.forces().cpu().numpy().astype(np.float64), cloud.forces().cpu().numpy().astype(np.float64)
+    assert rel_l2(Fs, Fo) <= 2e-6
+    assert torch.count_nonzero(cloud.acc).item() == 0          # integrate leaves the accumulators cleared
+    # pair part of the integrated force = accumulators (containment is added by the integrate pass)
+    far_from_edge = np.hypot(*cloud.pos[:n].cpu().numpy().T) < 90     # containment starts at 1.5 R = 97.7
+    assert far_from_edge.any()
+    Fs_sorted = cloud.force.cpu().numpy().astype(np.float64)
+    assert np.abs(Fs_sorted[far_from_edge] - F_sym[far_from_edge]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_large_cloud_sampled_against_oracle(scheme):
     """N = 200,000: sorted, tile-classified fast path; 384 sampled nucleons against the oracle."""
     from pyqmd_b200.state import NucleonCloud
     n = 200_000
     pos, isp = make_cloud(n, seed=11)
-    cloud = NucleonCloud(pos, isp, keep_force=True)
+    cloud = NucleonCloud(pos, isp, keep_force=True, scheme=scheme)
     cloud.step(1)
     F = cloud.forces().cpu().numpy().astype(np.float64)
     x = pos[:, 0].astype(np.float64); y = pos[:, 1].astype(np.float64)
@@ -153,11 +202,12 @@ def test_large_cloud_sampled_against_oracle():
     assert np.isfinite(F).all()
 
 
-def test_multi_step_cloud_teacher_forced():
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_multi_step_cloud_teacher_forced(scheme):
     from pyqmd_b200.state import NucleonCloud
     n = 1500
     pos, isp = make_cloud(n, seed=21, density=1 / 9)
-    cloud = NucleonCloud(pos, isp, keep_force=True, sort=False)
+    cloud = NucleonCloud(pos, isp, keep_force=True, sort=False, scheme=scheme)
     for s in range(4):
         p0 = cloud.pos[:n].cpu().numpy().copy()
         cloud.step(1)

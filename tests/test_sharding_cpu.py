@@ -92,3 +92,17 @@ def test_global_ids_make_sharding_invisible_to_the_rng():
         lo, hi = sharding.shard_range(n, r, world)
         parts.append(orc.philox_uniforms(99, lo, hi - lo, 3, 0))
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_symmetric_cloud_rows_partition_and_balance():
+    """Rows of the symmetric cloud scheme: every row owned by exactly one part, work balanced."""
+    from pyqmd_b200.sharding import sym_row_work, sym_rows_of
+    for n in (1, 1000, 4096, 200_000, 1_000_000):
+        nb = (n + 1023) // 1024
+        for parts in (1, 2, 3, 4, 8):
+            owned = [sym_rows_of(p, parts, n) for p in range(parts)]
+            flat = sorted(b for rows in owned for b in rows)
+            assert flat == list(range(nb)), (n, parts)
+            if n >= 200_000:
+                work = [sum(sym_row_work(b, n) for b in rows) for rows in owned]
+                assert max(work) <= 1.02 * (sum(work) / parts), (n, parts, work)
