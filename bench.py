@@ -310,66 +310,20 @@ def main():
             "data": "synthetic"}
     launches = 0
 
+    ens = tot_nuc = tot_pairs = None
     if args.workload in ("ensemble", "mixed"):
-        isotopes = (PB208,) if args.workload == "ensemble" else README_ISOTOPES
-        total = args.nuclei * world if args.nuclei else (N_ENSEMBLE * world if args.workload == "ensemble"
-                                                         else N_MIXED)
-        per = (total + world - 1) // world
-        lo = rank * per
-        n_mine = max(0, min(per, total - lo))
-        decay = args.workload == "mixed"
-        ens = NucleusEnsemble.from_templates(isotopes, n_mine, device=dev, id_base=lo, decay=decay,
-                                             dt_decay=180825048000.0 * 1e-3, seed=2024)
-        pairs_step = ens.pairs_per_step() * args.substeps
-        nucleons = int(ens.count.sum().item())
-        sample = range(0, ens.n_nuclei, max(1, ens.n_nuclei // 256))
-        flops0 = ens.census(sample)[1]
-        sec = timed_steps(lambda: ens.step(args.substeps), K, W, dist, torch, sampler)
+        res, ens, tot_nuc, tot_pairs = bench_ensemble(args, args.workload, K, W, rank, world, dev, dist,
+                                                      torch, sampler, fp32_peak,
+                                                      (f1.value, f2.value, nominal), hbm_peak, hbm_src,
+                                                      with_e2e=True)
+        line.update(res)
         clocks = sampler.result()
         launches = K * len(ens.bins)
-        census1, flops1 = ens.census(sample)
-        tot_pairs = torch.tensor([float(pairs_step)], device=dev, dtype=torch.float64)
-        tot_nuc = torch.tensor([float(ens.n_nuclei)], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(tot_pairs); dist.all_reduce(tot_nuc)
-        value = float(tot_pairs.item()) * K / sec
-        # e2e: host-buffer API, H2D + kernel + D2H every step
-        runner = HostEnsembleRunner(ens, chunks=8)
-        sec_e2e = timed_steps(lambda: runner.step(args.substeps), max(3, K // 4), 2, dist, torch)
-        e2e_value = float(tot_pairs.item()) * max(3, K // 4) / sec_e2e
-        flops_pair = 0.5 * (flops0 + flops1)
-        my_rate = pairs_step * K / sec          # this rank's kernel
-        line.update({
-            "value": value, "ms_per_step": sec / K * 1e3,
-            "scaling": "weak" if args.workload == "ensemble" and not args.nuclei else "strong",
-            "config": {"workload": ("C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one "
-                                    "nucleus per thread block" if args.workload == "ensemble" else
-                                    "C3 mixed ensemble of 1M nuclei over the nine preset isotopes, "
-                                    "decay on, sharded by nucleus"),
-                       "nuclei_total": int(tot_nuc.item()), "nucleons_per_gpu": nucleons,
-                       "substeps_per_step": args.substeps, "dt_phys": 1 / 240,
-                       "l2_policy": "inputs larger than L2 (state %.0f MB per GPU)" % (nucleons * 17 / 1e6),
-                       "parallelism": f"by-nucleus x{world}, no collective"},
-            "nucleus_steps_per_s": float(tot_nuc.item()) * args.substeps * K / sec,
-            "e2e": {"value": e2e_value, "unit": "pairs/s",
-                    "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
-                    "chunks": runner.n_chunks},
-            "roofline": {"bound": "fp32", "achieved": my_rate * flops_pair / 1e12, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": my_rate * flops_pair / 1e12 / fp32_peak,
-                         "traffic": ncu_traffic("ensemble_pair_kernel") if args.workload == "ensemble"
-                         and not args.nuclei and args.substeps == 1 else None,
-                         "kernel": "ensemble_pair_kernel",
-                         "flops_per_pair": flops_pair, "branch_census_end": census1,
-                         "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
-                                        "f32x2 %.1f TFLOP/s); nominal %.1f" % (f1.value, f2.value, nominal),
-                         "hbm_gbs": nucleons * 36 * args.substeps * K / sec / 1e9 / max(args.substeps, 1),
-                         "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
-        })
     elif args.workload == "cloud":
         line.update(bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak,
                                 (f1.value, f2.value, nominal)))
         clocks = sampler.result()
-        launches = K * 3
+        launches = K * 4
     else:
         line.update(bench_decay(args, K, W, rank, world, dev, dist, torch, sampler, hbm_peak, hbm_src))
         clocks = sampler.result()
@@ -387,11 +341,25 @@ def main():
                  "nucleus_frames_per_s": float(tot_nuc.item()) * 5 / sec_f,
                  "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 5 / sec_f,
                  "note": "4 sub-steps + resolve_overlaps per frame, device resident"}
+        del ens
+        torch.cuda.empty_cache()
+        keep = ("metric", "unit", "value", "ms_per_step", "config", "roofline", "scaling",
+                "nucleus_steps_per_s", "decays")
+        also = {"frame": frame}
         extra = bench_cloud(args, 2, 1, rank, world, dev, dist, torch, None, fp32_peak,
                             (f1.value, f2.value, nominal))
-        line["also"] = {"frame": frame,
-                        "cloud": {k: extra[k] for k in ("value", "ms_per_step", "config", "roofline",
-                                                        "scaling")}}
+        also["cloud"] = {k: extra[k] for k in keep if k in extra}
+        torch.cuda.empty_cache()
+        extra, ens3, _, _ = bench_ensemble(args, "mixed", 5, 3, rank, world, dev, dist, torch, None,
+                                           fp32_peak, (f1.value, f2.value, nominal), hbm_peak, hbm_src,
+                                           with_e2e=False)
+        also["mixed"] = {k: extra[k] for k in keep if k in extra}
+        del ens3
+        torch.cuda.empty_cache()
+        extra = bench_decay(args, 3, 3, rank, world, dev, dist, torch, None, hbm_peak, hbm_src)
+        also["decay"] = {k: extra[k] for k in keep if k in extra}
+        torch.cuda.empty_cache()
+        line["also"] = also
 
     if rank == 0 and world == 1:
         from oracle import oracle as orc
@@ -413,6 +381,76 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_ensemble(args, workload, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, peak_info,
+                   hbm_peak, hbm_src, with_e2e):
+    """C2 (``ensemble``: 65,536 Pb-208 per GPU, weak) or C3 (``mixed``: 1M nuclei over the nine
+    preset isotopes in total, decay on, strong)."""
+    from pyqmd_b200.state import README_ISOTOPES, HostEnsembleRunner, NucleusEnsemble
+    isotopes = (PB208,) if workload == "ensemble" else README_ISOTOPES
+    total = args.nuclei * world if args.nuclei else (N_ENSEMBLE * world if workload == "ensemble"
+                                                     else N_MIXED)
+    per = (total + world - 1) // world
+    lo = rank * per
+    n_mine = max(0, min(per, total - lo))
+    decay = workload == "mixed"
+    ens = NucleusEnsemble.from_templates(isotopes, n_mine, device=dev, id_base=lo, decay=decay,
+                                         dt_decay=180825048000.0 * 1e-3, seed=2024)
+    pairs_step = ens.pairs_per_step() * args.substeps
+    nucleons = int(ens.count.sum().item())
+    import math
+    stride = max(1, ens.n_nuclei // 256)
+    while math.gcd(stride, len(isotopes)) != 1:      # isotopes cycle with the nucleus id: hit them all
+        stride += 1
+    sample = range(0, ens.n_nuclei, stride)
+    flops0 = ens.census(sample)[1]
+    sec = timed_steps(lambda: ens.step(args.substeps), K, W, dist, torch, sampler)
+    census1, flops1 = ens.census(sample)
+    tot_pairs = torch.tensor([float(pairs_step)], device=dev, dtype=torch.float64)
+    tot_nuc = torch.tensor([float(ens.n_nuclei)], device=dev, dtype=torch.float64)
+    decays = ens.mode_counts.clone()
+    if dist is not None:
+        dist.all_reduce(tot_pairs); dist.all_reduce(tot_nuc); dist.all_reduce(decays)
+    value = float(tot_pairs.item()) * K / sec
+    flops_pair = 0.5 * (flops0 + flops1)
+    my_rate = pairs_step * K / sec          # this rank's kernel
+    res = {
+        "value": value, "ms_per_step": sec / K * 1e3,
+        "scaling": "weak" if workload == "ensemble" and not args.nuclei else "strong",
+        "config": {"workload": ("C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one "
+                                "nucleus per thread block" if workload == "ensemble" else
+                                "C3 mixed ensemble of 1M nuclei over the nine preset isotopes, "
+                                "decay on, sharded by nucleus"),
+                   "nuclei_total": int(tot_nuc.item()), "nucleons_per_gpu": nucleons,
+                   "substeps_per_step": args.substeps, "dt_phys": 1 / 240,
+                   "l2_policy": "inputs larger than L2 (state %.0f MB per GPU)" % (nucleons * 17 / 1e6),
+                   "parallelism": f"by-nucleus x{world}, no collective"},
+        "nucleus_steps_per_s": float(tot_nuc.item()) * args.substeps * K / sec,
+        "roofline": {"bound": "fp32", "achieved": my_rate * flops_pair / 1e12, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": my_rate * flops_pair / 1e12 / fp32_peak,
+                     "traffic": ncu_traffic("ensemble_pair_kernel") if workload == "ensemble"
+                     and not args.nuclei and args.substeps == 1 else None,
+                     "kernel": "ensemble_pair_kernel",
+                     "flops_per_pair": flops_pair, "branch_census_end": census1,
+                     "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
+                                    "f32x2 %.1f TFLOP/s); nominal %.1f" % peak_info,
+                     "hbm_gbs": nucleons * 36 * args.substeps * K / sec / 1e9 / max(args.substeps, 1),
+                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
+    }
+    if decay:
+        res["decays"] = {"total_events": int(decays.sum().item()),
+                         "by_mode": [int(v) for v in decays.tolist()]}
+    if with_e2e:
+        # e2e: host-buffer API, H2D + kernel + D2H every step
+        runner = HostEnsembleRunner(ens, chunks=8)
+        k2 = max(3, K // 4)
+        sec_e2e = timed_steps(lambda: runner.step(args.substeps), k2, 2, dist, torch)
+        res["e2e"] = {"value": float(tot_pairs.item()) * k2 / sec_e2e, "unit": "pairs/s",
+                      "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
+                      "chunks": runner.n_chunks}
+        del runner
+    return res, ens, tot_nuc, tot_pairs
 
 
 def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, peak_info):
@@ -437,7 +475,12 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
                                    f"i-block x{world}")},
         "roofline": {"bound": "fp32", "achieved": mine * flops_pair / 1e12, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak, "traffic": None,
-                     "kernel": "cloud_force_kernel", "flops_per_pair": flops_pair,
+                     "kernel": "cloud_sym_kernel" if args.cloud_scheme == "symmetric" else "cloud_force_kernel",
+                     "flops_per_pair": flops_pair,
+                     "executed_pair_evaluations_per_step": pairs / 2 if args.cloud_scheme == "symmetric" else pairs,
+                     "note": ("algorithmic FLOPs of all N(N-1) ordered pairs (SURVEY 8d) over time; the "
+                              "symmetric scheme evaluates each unordered pair once, so frac may exceed 1"
+                              if args.cloud_scheme == "symmetric" else "ordered pairs, each evaluated"),
                      "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, f32x2 %.1f "
                                     "TFLOP/s); nominal %.1f" % peak_info},
     }
