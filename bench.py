@@ -359,6 +359,8 @@ def main():
         extra = bench_decay(args, 3, 3, rank, world, dev, dist, torch, None, hbm_peak, hbm_src)
         also["decay"] = {k: extra[k] for k in keep if k in extra}
         torch.cuda.empty_cache()
+        if rank == 0:
+            also["c1"] = bench_c1(dev, torch)
         line["also"] = also
 
     if rank == 0 and world == 1:
@@ -451,6 +453,64 @@ def bench_ensemble(args, workload, K, W, rank, world, dev, dist, torch, sampler,
                       "chunks": runner.n_chunks}
         del runner
     return res, ens, tot_nuc, tot_pairs
+
+
+def bench_c1(dev, torch):
+    """C1: one U-238 nucleus (configs[0]), 1000 force+integrate(+decay test) steps.
+    (a) through the reference-shaped drop-in NuclearForces.update_particles_cpu(list[Particle], dt),
+        one host round trip per sub-step, exactly how nuclear_sim.py:171-173 calls it;
+    (b) the same 1000 sub-steps fused into one call (NuclearForces.step);
+    (c) device resident (NucleusEnsemble of one nucleus, 1000 sub-steps in one launch, decay on)."""
+    import random
+    from pyqmd_b200.forces import NuclearForces
+    from pyqmd_b200.state import NucleusEnsemble, layout_templates
+    from pyqmd_b200.types import Particle, ParticleType
+    tm = layout_templates()
+    xy, isp = tm["z92_n146_xy"][0], tm["z92_n146_isp"][0]
+    mk = lambda: [Particle(400.0 + float(x), 400.0 + float(y),
+                           ParticleType.PROTON if t else ParticleType.NEUTRON) for (x, y), t in zip(xy, isp)]
+    nf = NuclearForces()
+    pairs = 238 * 237
+    ps = mk()
+    for _ in range(5):
+        nf.update_particles_cpu(ps, 1 / 240)
+    t0 = time.perf_counter()
+    calls = 200
+    for _ in range(calls):
+        nf.update_particles_cpu(ps, 1 / 240)
+    per_call = (time.perf_counter() - t0) / calls
+    ps = mk()
+    nf.step(ps, 1 / 240, 10)
+    t0 = time.perf_counter()
+    nf.step(ps, 1 / 240, 1000)
+    fused = time.perf_counter() - t0
+    ens = NucleusEnsemble.from_templates(((92, 146),), 1, device=dev, decay=True,
+                                         dt_decay=1.409993568e17 * 1e-3, seed=1)
+    ens.step(10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ens.step(1000)
+    e1.record()
+    torch.cuda.synchronize()
+    resident = e0.elapsed_time(e1) * 1e-3
+    from oracle import oracle as orc
+    x, y = xy[:, 0].astype(np.float64), xy[:, 1].astype(np.float64)
+    t0 = time.perf_counter()
+    orc.ensemble_force_steps(np.array([0], np.int64), np.array([238], np.int32), x, y, np.zeros(238),
+                             np.zeros(238), isp, 1 / 240, 200, n_threads=1)
+    cpu = (time.perf_counter() - t0) / 200
+    return {"config": {"workload": "C1 single U-238 nucleus (238 nucleons), 1000 sub-steps"},
+            "cpu_port_1core": {"ms_per_substep": cpu * 1e3, "pairs_per_s": pairs / cpu,
+                               "note": "C oracle port, one core (one nucleus does not parallelise)"},
+            "dropin_per_substep_call": {"ms_per_call": per_call * 1e3, "pairs_per_s": pairs / per_call,
+                                        "api": "NuclearForces.update_particles_cpu(list[Particle], dt)"},
+            "dropin_fused_1000": {"ms_total": fused * 1e3, "pairs_per_s": pairs * 1000 / fused,
+                                  "api": "NuclearForces.step(list[Particle], dt, 1000)"},
+            "device_resident_1000": {"ms_total": resident * 1e3, "pairs_per_s": pairs * 1000 / resident,
+                                     "nucleus_steps_per_s": 1000 / resident,
+                                     "api": "NucleusEnsemble.step(1000), decay test on"},
+            "reference_python_cpu": "75-91 ms per sub-step (SURVEY.md section 6 [probe]), 6.2-7.5e5 pairs/s"}
 
 
 def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, peak_info):
