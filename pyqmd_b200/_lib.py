@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libpyqmd_b200.so")
+SO_PATH = os.environ.get("PYQMD_B200_LIB") or os.path.join(HERE, "libpyqmd_b200.so")   # override: tuning builds
 
 TABLE_ZDIM = 128
 TABLE_NDIM = 192

@@ -38,13 +38,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = SO) -> str:
+    """``defines`` / ``out``: tuning builds (A/B variants selected with PYQMD_B200_LIB)."""
+    if not force and not is_stale() and out == SO:
         return SO
-    cmd = [nvcc_path(), *NVCC_FLAGS]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines]]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", SO]
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -53,8 +54,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpyqmd_b200.so")
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="--verbose" in sys.argv,
+                defines=defs, out=os.path.abspath(outs[0]) if outs else SO))

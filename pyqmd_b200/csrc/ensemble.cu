@@ -378,8 +378,11 @@ __device__ __forceinline__ void publish_pair_sums(float4* wsum, int capT, int g,
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = make_float4(a, b, c, d);
 }
 
+#ifndef PYQMD_ENS_MINBLOCKS
+#define PYQMD_ENS_MINBLOCKS 4      // A/B on B200: 2 -> 1.01e12, 3 -> 1.07e12, 4 -> 1.12e12, 5 -> spills
+#endif
 template <int MAXT, bool SCALAR = false>
-__global__ void __launch_bounds__(MAXT, 3) ensemble_pair_kernel(const pyqmd_ensemble e,
+__global__ void __launch_bounds__(MAXT, PYQMD_ENS_MINBLOCKS) ensemble_pair_kernel(const pyqmd_ensemble e,
                                                               const LawParams L, const int n_steps,
                                                               const int G, const int capT)
 {
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(MAXT, 3) ensemble_pair_kernel(const pyqmd_ense
                     const float sb = pair_general(dxb, dyb, t1, tt.x, L);
                     const float pxa = dxa * sa, pya = dya * sa, pxb = dxb * sb, pyb = dyb * sb;
                     sfx0 += pxa; sfy0 += pya; sfx1 += pxb; sfy1 += pyb;
-                    const int ur = (u >= m) ? u - m : u;
+                    const unsigned ur = min((unsigned)u, (unsigned)(u - m));
                     float2 r = row[par * capT_ + ur];
                     r.x -= pxa + pxb;
                     r.y -= pya + pyb;
@@ -573,11 +576,13 @@ __global__ void __launch_bounds__(MAXT, 3) ensemble_pair_kernel(const pyqmd_ense
                 float pa, pb, qa, qb;
                 upk(px2, pa, pb);
                 upk(py2, qa, qb);
-                const int ur = (u >= m) ? u - m : u;
-                float2 r = row[par * capT_ + ur];            // reaction on the partner
+                // u < 2m: un-mirror with one unsigned min (u - m wraps to a huge value when u < m)
+                const unsigned ur = min((unsigned)u, (unsigned)(u - m));
+                float2* rp = row + par * capT_ + ur;         // reaction on the partner
+                float2 r = *rp;
                 r.x -= pa + pb;
                 r.y -= qa + qb;
-                row[par * capT_ + ur] = r;
+                *rp = r;
             };
             const int hs = (m - 1) >> 1;
             for (int k = 1; k <= hs; ++k) {
@@ -712,7 +717,7 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
                                                       cudaSharedmemCarveoutMaxShared));
                 attr_set = true;
             }
-            // blocks of <= 224 threads get 96 registers per thread at 3 blocks / SM
+            // blocks of <= 224 threads: 4 blocks / SM at 72 registers per thread
             static int scalar_ab = -1;
             if (scalar_ab < 0) scalar_ab = getenv("PYQMD_ENS_SCALAR") ? 1 : 0;
             if (scalar_ab) {

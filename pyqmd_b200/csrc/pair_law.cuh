@@ -140,12 +140,17 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
     return (d2 < kSkipD2) ? 0.0f : s;                             // [257]
 }
 
+#ifndef PYQMD_GEN_FOLD_COEF
+#define PYQMD_GEN_FOLD_COEF 1      // A/B on B200 (C2): +5 %
+#endif
+
 // Two general pairs at once: nucleons (i_a, i_b) of one thread against the same partner j, all
 // FMA-pipe arithmetic packed (f32x2), compares / selects / min-max / MUFU per element.
 //   dx, dy = (r_j - r_ia, r_j - r_ib);  tj2 = (t_j, t_j);  nq = (-C t_ia, -C t_ib).
 // Same arithmetic as pair_general.
 struct GenConsts {
     f32x2 nInvHard, one, eps, negCoreK, n60, negP, kPauli;
+    f32x2 kAttr, lAttr, kTail, lTail;      // 2^(k d + l) forms of the attractive / tail strong terms
 };
 
 __device__ __forceinline__ GenConsts make_gen_consts(const LawParams& L)
@@ -158,6 +163,10 @@ __device__ __forceinline__ GenConsts make_gen_consts(const LawParams& L)
     c.n60 = pk1(-60.0f);
     c.negP = pk1(-L.P);
     c.kPauli = pk1(-2.0f * kLog2e / kPauliD);
+    c.kAttr = pk1(-kLog2e / 7.0f);
+    c.kTail = pk1(-1.8f * kLog2e / 7.0f);
+    c.lAttr = pk1(L.attrK > 0.f ? log2f(L.attrK) : -150.f);
+    c.lTail = pk1(L.log2TailK);
     return c;
 }
 
@@ -178,11 +187,28 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     const f32x2 hc = mul2(pk(ova, ovb), pk(mufu_sqrt(ova), mufu_sqrt(ovb)));
     // strong                                                        [273-281]
     const f32x2 a = add2(d, c.eps), b = add2(d2, c.eps);
+#ifdef PYQMD_GEN_TWO_RCP
+    float aa, ab, ba, bb;
+    upk(a, aa, ab);
+    upk(b, ba, bb);
+    const f32x2 inv_a = pk(mufu_rcp(aa), mufu_rcp(ab)), inv_b = pk(mufu_rcp(ba), mufu_rcp(bb));
+#else
     float aba, abb;
     upk(mul2(a, b), aba, abb);
     const f32x2 rab = pk(mufu_rcp(aba), mufu_rcp(abb));
     const f32x2 inv_a = mul2(rab, b), inv_b = mul2(rab, a);
+#endif
     const bool attr_a = d2a < kAttrD * kAttrD, attr_b = d2b < kAttrD * kAttrD;
+#if PYQMD_GEN_FOLD_COEF
+    // coefficient folded into the exponent: coef * 2^(k d) = 2^(k d + log2 coef); both candidate
+    // arguments are computed packed, one select per element picks the branch
+    float xa, xb, ya, yb;
+    upk(fma2(d, c.kAttr, c.lAttr), xa, xb);
+    upk(fma2(d, c.kTail, c.lTail), ya, yb);
+    const f32x2 e = pk(mufu_ex2(attr_a ? xa : ya), mufu_ex2(attr_b ? xb : yb));
+    float sfa, sfb, sca, scb;
+    upk(mul2(e, inv_a), sfa, sfb);
+#else
     const f32x2 kexp = pk(attr_a ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f),
                           attr_b ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f));
     const f32x2 coef = pk(attr_a ? L.attrK : L.tailK, attr_b ? L.attrK : L.tailK);
@@ -191,6 +217,7 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     const f32x2 e = pk(mufu_ex2(ea), mufu_ex2(eb));
     float sfa, sfb, sca, scb;
     upk(mul2(mul2(coef, e), inv_a), sfa, sfb);
+#endif
     upk(mul2(c.negCoreK, inv_b), sca, scb);
     const f32x2 strong = pk(d2a < kCoreD * kCoreD ? sca : sfa, d2b < kCoreD * kCoreD ? scb : sfb);
     f32x2 net = fma2(hc, c.n60, strong);
