@@ -534,7 +534,8 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
                                    f"all-gather" if args.cloud_scheme == "symmetric" and world > 1 else
                                    f"i-block x{world}")},
         "roofline": {"bound": "fp32", "achieved": mine * flops_pair / 1e12, "peak": fp32_peak,
-                     "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak,
+                     "traffic": None,   # ncu capture is at N = 262,144 (profiles/traffic.json): 6.9 MB per launch
                      "kernel": "cloud_sym_kernel" if args.cloud_scheme == "symmetric" else "cloud_force_kernel",
                      "flops_per_pair": flops_pair,
                      "executed_pair_evaluations_per_step": pairs / 2 if args.cloud_scheme == "symmetric" else pairs,

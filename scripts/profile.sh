@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:ensemble -s 1 -c
     -f -o gpurun_out/prof_ensemble_${TAG} python bench.py --steps 2 --warmup 1 --no-extras \
     > gpurun_out/ncu_ens_${TAG}.log 2>&1
 python bench.py --workload cloud --cloud-n 262144 --steps 1 --warmup 1 > gpurun_out/plain3_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cloud_force_kernel -s 1 -c 1 \
+ncu --set full --clock-control none --import-source on -k "regex:cloud_sym_kernel|cloud_force_kernel" -s 1 -c 1 \
     -f -o gpurun_out/prof_cloud_${TAG} python bench.py --workload cloud --cloud-n 262144 --steps 1 --warmup 1 \
     > gpurun_out/ncu_cloud_${TAG}.log 2>&1
 ls -la gpurun_out
