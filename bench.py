@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--nuclei", type=int, default=0, help="override nuclei per GPU (ensemble/mixed)")
     ap.add_argument("--cloud-n", type=int, default=N_CLOUD)
+    ap.add_argument("--cloud-exchange", default="peer", choices=["peer", "nccl"],
+                    help="symmetric scheme on several GPUs: fused peer-memory kernel, or NCCL collectives")
     ap.add_argument("--cloud-scheme", default="symmetric", choices=["symmetric", "ordered"],
                     help="symmetric: every unordered pair once + integer force reduce-scatter; "
                          "ordered: i-block rows x all j, position all-gather only")
@@ -517,7 +519,8 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
     from pyqmd_b200.state import NucleonCloud
     n = args.cloud_n
     pos, isp = make_cloud(n)
-    cloud = NucleonCloud(pos, isp, device=dev, rank=rank, world=world, scheme=args.cloud_scheme)
+    cloud = NucleonCloud(pos, isp, device=dev, rank=rank, world=world, scheme=args.cloud_scheme,
+                         exchange=args.cloud_exchange)
     sec = timed_steps(lambda: cloud.step(1), K, W, dist, torch, sampler)
     pairs = float(n) * (n - 1)
     f_pp = (float(isp.sum()) / n) ** 2
@@ -529,10 +532,12 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
                                f"i-block sharded x{world}" + (" + NCCL position all-gather" if world > 1 else ""),
                    "l2_policy": "per-step working set (positions 8N B) is L2 resident by design; "
                                 "compute bound", "dt_phys": 1 / 240,
-                   "scheme": args.cloud_scheme,
-                   "parallelism": (f"i-block rows dealt x{world}, integer force reduce-scatter + position "
-                                   f"all-gather" if args.cloud_scheme == "symmetric" and world > 1 else
-                                   f"i-block x{world}")},
+                   "scheme": args.cloud_scheme, "exchange": cloud.exchange,
+                   "parallelism": (f"i-block rows dealt x{world}; integer force reduce-scatter + integrate + "
+                                   f"position all-gather " + ("fused in one peer-memory kernel (NVLink)"
+                                                              if cloud.exchange == "peer" else "via NCCL")
+                                   if args.cloud_scheme == "symmetric" and world > 1 else
+                                   f"i-block x{world}" + (" + NCCL position all-gather" if world > 1 else ""))},
         "roofline": {"bound": "fp32", "achieved": mine * flops_pair / 1e12, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak,
                      "traffic": None,   # ncu capture is at N = 262,144 (profiles/traffic.json): 6.9 MB per launch

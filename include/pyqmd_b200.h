@@ -127,6 +127,21 @@ int pyqmd_cloud_integrate(const float *pos_in, float *pos_out, float *vel, float
                           int64_t i0, int64_t i1, float dt, long long *force_acc_i0,
                           void *workspace, void *stream);
 
+/*
+ * Multi-GPU epilogue of the symmetric scheme over PEER MEMORY (NVLink / NVSwitch, no collective
+ * library on the data path): reduce-scatter of the force accumulators + integrate + all-gather of
+ * the new positions in one kernel.  acc_peers / pos_out_peers are DEVICE arrays of n_peers
+ * pointers: rank p's accumulator array (int64[n][2]) and rank p's replica of the next positions
+ * (float2[n]), all mapped into this process (CUDA IPC / symmetric memory).  The owner of [i0, i1)
+ * pulls and clears acc_peers[p][i], integrates (:301-323) and stores the new position into every
+ * pos_out_peers[p][i].  The caller must barrier all ranks before (every pyqmd_cloud_pair_forces
+ * finished) and after (every push landed) the call.
+ */
+int pyqmd_cloud_exchange_integrate(const float *pos_in, float *vel, float *force, int64_t n,
+                                   int64_t i0, int64_t i1, float dt, long long *const *acc_peers,
+                                   float *const *pos_out_peers, int32_t n_peers, void *workspace,
+                                   void *stream);
+
 /* 64-bit sort keys: bit 63 = neutron, low bits = 2-D Morton code of the position inside
  * [xmin, xmin+extent) x [ymin, ymin+extent).  Sorting by key gives the layout above. */
 int pyqmd_cloud_sort_keys(const float *pos, const uint8_t *is_proton, int64_t n, float xmin,

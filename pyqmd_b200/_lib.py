@@ -25,6 +25,7 @@ EXPORTS = (
     "pyqmd_update_forces_and_positions", "pyqmd_update_particles_f64",
     "pyqmd_cloud_workspace_bytes", "pyqmd_cloud_step", "pyqmd_cloud_sort_keys",
     "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_integrate",
+    "pyqmd_cloud_exchange_integrate",
     "pyqmd_ensemble_step", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
     "pyqmd_population_step",
 )
@@ -102,6 +103,7 @@ def lib():
     L.pyqmd_cloud_force_scale_log2.argtypes = [i64]
     L.pyqmd_cloud_pair_forces.argtypes = [vp, vp, i64, i32, i32, f32, f32, f32, vp, vp, vp]
     L.pyqmd_cloud_integrate.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, vp, vp, vp]
+    L.pyqmd_cloud_exchange_integrate.argtypes = [vp, vp, vp, i64, i64, i64, f32, vp, vp, i32, vp, vp]
     L.pyqmd_ensemble_step.argtypes = [C.POINTER(EnsembleDesc), i32, vp]
     L.pyqmd_resolve_overlaps.argtypes = [C.POINTER(EnsembleDesc), vp, i32, vp, vp]
     L.pyqmd_ensemble_census.argtypes = [C.POINTER(EnsembleDesc), vp, vp]

@@ -353,6 +353,43 @@ cloud_sym_integrate_kernel(const float2* __restrict__ pos_in, float2* __restrict
     if (force) force[i] = make_float2(Fx, Fy);
 }
 
+// Fused exchange + integrate for several GPUs (peer memory over NVLink, no NCCL on the data path):
+// the owner of [i0, i1) PULLS the int64 force accumulators of its nucleons from every rank (16-byte
+// peer loads), sums them (integer: exact, order-independent), clears the consumed entries on the
+// peers, integrates, and PUSHES the new positions into every rank's replica (8-byte peer stores) --
+// i.e. reduce-scatter(forces) + integrate + all-gather(positions) in one kernel.  The caller
+// brackets it with two device-side barriers (all pair-force kernels done / all pushes landed).
+__global__ void __launch_bounds__(256)
+cloud_sym_exchange_integrate_kernel(const float2* __restrict__ pos_in, float2* __restrict__ vel,
+                                    float2* __restrict__ force, int64_t n, int64_t i0, int64_t i1,
+                                    CloudWorkspace w, long long* const* __restrict__ acc_peers,
+                                    float2* const* __restrict__ pos_out_peers, int n_peers,
+                                    float inv_scale, float dt)
+{
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    long long sx = 0, sy = 0;
+    for (int p = 0; p < n_peers; ++p) {
+        longlong2* a = reinterpret_cast<longlong2*>(acc_peers[p]) + i;
+        const longlong2 v = *a;
+        *a = make_longlong2(0, 0);
+        sx += v.x;
+        sy += v.y;
+    }
+    float Fx = (float)((double)sx * (double)inv_scale);
+    float Fy = (float)((double)sy * (double)inv_scale);
+    const float cx = (float)w.centre[0], cy = (float)w.centre[1];
+    const float R = 2.4f * cbrtf((float)n);            // :304
+    const float2 p0 = pos_in[i];
+    float2 vv = vel[i];
+    float x = p0.x, y = p0.y;
+    contain_and_integrate(x, y, vv.x, vv.y, Fx, Fy, cx, cy, R, dt);
+    vel[i] = vv;
+    if (force) force[i] = make_float2(Fx, Fy);
+    const float2 out = make_float2(x, y);
+    for (int p = 0; p < n_peers; ++p) pos_out_peers[p][i] = out;
+}
+
 int cloud_prepass(const float* pos, const uint8_t* is_proton, int64_t n, const CloudWorkspace& w,
                   cudaStream_t st);
 
@@ -425,6 +462,26 @@ extern "C" int pyqmd_cloud_integrate(const float* pos_in, float* pos_out, float*
         reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(pos_out),
         reinterpret_cast<float2*>(vel), reinterpret_cast<float2*>(force), n, i0, i1, w, force_acc_i0,
         inv_scale, dt);
+    PYQMD_CUDA_CHECK(cudaGetLastError());
+    return PYQMD_OK;
+}
+
+extern "C" int pyqmd_cloud_exchange_integrate(const float* pos_in, float* vel, float* force, int64_t n,
+                                              int64_t i0, int64_t i1, float dt,
+                                              long long* const* acc_peers, float* const* pos_out_peers,
+                                              int32_t n_peers, void* workspace, void* stream)
+{
+    PYQMD_REQUIRE(n >= 0 && i0 >= 0 && i0 <= i1 && i1 <= n, "0 <= i0 <= i1 <= n");
+    PYQMD_REQUIRE(n_peers >= 1, "n_peers >= 1");
+    if (n == 0 || i0 == i1) return PYQMD_OK;
+    PYQMD_REQUIRE(pos_in && vel && acc_peers && pos_out_peers && workspace, "NULL pointer");
+    const CloudWorkspace w = carve(workspace, n);
+    const float inv_scale = ldexpf(1.0f, -scale_log2_for(n));
+    cloud_sym_exchange_integrate_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0,
+                                          (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(pos_in), reinterpret_cast<float2*>(vel),
+        reinterpret_cast<float2*>(force), n, i0, i1, w, acc_peers,
+        reinterpret_cast<float2* const*>(pos_out_peers), n_peers, inv_scale, dt);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }

@@ -376,13 +376,23 @@ class NucleonCloud:
         exact, order-independent totals of its own block.
     scheme="ordered": rank r evaluates the ordered pairs (i, j) for its own i only (the
         decomposition BASELINE.json names: i-block + position all-gather, no force exchange).
+
+    exchange (symmetric scheme, world > 1):
+      "peer" (default): accumulators and position replicas live in symmetric memory
+        (torch.distributed._symmetric_memory: every rank maps every peer's buffers over NVLink);
+        ONE kernel per step pulls + sums + clears the accumulators of the rank's block from all
+        peers, integrates, and pushes the new positions into all replicas
+        (pyqmd_cloud_exchange_integrate), bracketed by two device-side barriers.  No NCCL call on
+        the data path.  Falls back to "nccl" (with a warning) if symmetric memory cannot be set up.
+      "nccl": reduce_scatter_tensor(int64 SUM) -> integrate -> all_gather_into_tensor.
+    Both exchanges give bit-identical results (integer sums).
     """
 
     def __init__(self, pos, is_proton, vel=None, *, device="cuda", dt=DEFAULT_DT,
                  strengths=DEFAULT_STRENGTHS, rank=0, world=1, group=None, sort=True,
-                 keep_force=False, scheme="symmetric"):
+                 keep_force=False, scheme="symmetric", exchange="peer"):
         _lib.require_cuda()
-        assert scheme in ("symmetric", "ordered")
+        assert scheme in ("symmetric", "ordered") and exchange in ("peer", "nccl")
         dev = self.device = torch.device(device)
         pos = torch.as_tensor(pos, dtype=torch.float32).reshape(-1, 2).to(dev)
         isp = torch.as_tensor(is_proton, dtype=torch.uint8).to(dev)
@@ -399,8 +409,18 @@ class NucleonCloud:
             self.perm = self._sort_perm(pos, isp)
             pos, vel, isp = pos[self.perm].contiguous(), vel[self.perm].contiguous(), isp[self.perm].contiguous()
         padded = self.chunk * self.world
-        self.pos = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
-        self.pos_next = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
+        self.exchange = exchange if (self.world > 1 and scheme == "symmetric") else None
+        self._symm = None
+        if self.exchange == "peer":
+            try:
+                self._setup_peer_buffers(padded)
+            except Exception as exc:             # noqa: BLE001 -- any failure: use the NCCL exchange
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({exc!r}); using the NCCL exchange")
+                self.exchange, self._symm = "nccl", None
+        if self._symm is None:
+            self.pos = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
+            self.pos_next = torch.zeros(padded, 2, device=dev, dtype=torch.float32)
         self.pos[: self.n] = pos
         self.vel = vel.contiguous()
         self.is_proton = isp.contiguous()
@@ -408,13 +428,36 @@ class NucleonCloud:
         ws = int(_lib.lib().pyqmd_cloud_workspace_bytes(self.n))
         self.workspace = torch.zeros(max(ws, 64), dtype=torch.uint8, device=dev)
         # fixed-point force accumulators of the symmetric scheme (kept zero between steps)
-        self.acc = self.acc_mine = None
-        if scheme == "symmetric":
-            self.acc = torch.zeros(padded, 2, device=dev, dtype=torch.int64)
-            self.acc_mine = (torch.zeros(self.chunk, 2, device=dev, dtype=torch.int64)
-                             if self.world > 1 else self.acc)
+        if self._symm is None:
+            self.acc = self.acc_mine = None
+            if scheme == "symmetric":
+                self.acc = torch.zeros(padded, 2, device=dev, dtype=torch.int64)
+                self.acc_mine = (torch.zeros(self.chunk, 2, device=dev, dtype=torch.int64)
+                                 if self.world > 1 else self.acc)
         self.force_scale_log2 = int(_lib.lib().pyqmd_cloud_force_scale_log2(max(self.n, 1)))
         self.steps_done = 0
+
+    def _setup_peer_buffers(self, padded):
+        """acc + both position replicas in symmetric memory; device arrays of the peers' pointers."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        dev = self.device
+        bufs, hdls = {}, {}
+        for name, dtype in (("acc", torch.int64), ("pos_a", torch.float32), ("pos_b", torch.float32)):
+            t = symm_mem.empty(padded, 2, dtype=dtype, device=dev)
+            hdl = symm_mem.rendezvous(t, group)
+            t.zero_()
+            bufs[name], hdls[name] = t, hdl
+        assert hdls["acc"].world_size == self.world and hdls["acc"].rank == self.rank
+        self.acc, self.acc_mine = bufs["acc"], None
+        self.pos, self.pos_next = bufs["pos_a"], bufs["pos_b"]
+        ptrs = lambda h: torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=dev)
+        self._symm = {"hdl": hdls, "acc_ptrs": ptrs(hdls["acc"]),
+                      "pos_ptrs": {bufs["pos_a"].data_ptr(): ptrs(hdls["pos_a"]),
+                                   bufs["pos_b"].data_ptr(): ptrs(hdls["pos_b"])}}
+        torch.cuda.synchronize(dev)
+        hdls["acc"].barrier(channel=0)           # every rank's buffers are zeroed before the first step
 
     def _sort_perm(self, pos, isp):
         lo = pos.min(0).values
@@ -442,6 +485,20 @@ class NucleonCloud:
                     self.pos.data_ptr(), self.is_proton.data_ptr(), self.n, self.rank, self.world,
                     S, Cc, P, self.acc.data_ptr(), self.workspace.data_ptr(), stream),
                     "pyqmd_cloud_pair_forces")
+                if self._symm is not None:
+                    # peer-memory exchange fused with the integration (no NCCL on the data path)
+                    hdl = self._symm["hdl"]["acc"]
+                    hdl.barrier(channel=0)       # all pair-force kernels finished
+                    _lib.check(lib.pyqmd_cloud_exchange_integrate(
+                        self.pos.data_ptr(), self.vel.data_ptr(), _lib.ptr(self.force), self.n,
+                        self.i0, self.i1, self.dt, self._symm["acc_ptrs"].data_ptr(),
+                        self._symm["pos_ptrs"][self.pos_next.data_ptr()].data_ptr(), self.world,
+                        self.workspace.data_ptr(), _lib.current_stream()),
+                        "pyqmd_cloud_exchange_integrate")
+                    hdl.barrier(channel=1)       # all pushes landed, all consumed entries cleared
+                    self.pos, self.pos_next = self.pos_next, self.pos
+                    self.steps_done += 1
+                    continue
                 if self.world > 1:
                     dist.reduce_scatter_tensor(self.acc_mine, self.acc, op=dist.ReduceOp.SUM,
                                                group=self.group)

@@ -20,17 +20,19 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 150_001
 pos, isp = make_cloud(n, seed=99)
 out = {"n": n, "world": world}
-for scheme in ("symmetric", "ordered"):
-    multi = NucleonCloud(pos, isp, device=f"cuda:{local}", rank=rank, world=world, scheme=scheme)
+for scheme, exchange in (("symmetric", "peer"), ("symmetric", "nccl"), ("ordered", "nccl")):
+    multi = NucleonCloud(pos, isp, device=f"cuda:{local}", rank=rank, world=world, scheme=scheme,
+                         exchange=exchange)
+    used = multi.exchange
+    scheme = scheme if scheme == "ordered" else f"symmetric_{exchange}"
     multi.step(3)
     torch.cuda.synchronize()
     if rank == 0:
-        single = NucleonCloud(pos, isp, device="cuda:0", scheme=scheme)
+        single = NucleonCloud(pos, isp, device="cuda:0", scheme=scheme.split("_")[0])
         single.step(3)
         a, b = multi.pos[:n], single.pos[:n]
         out[scheme] = {"bit_identical": bool(torch.equal(a, b)),
-                       "max_abs_diff": float((a - b).abs().max()),
-                       "vel_identical": None}
+                       "max_abs_diff": float((a - b).abs().max()), "exchange_used": used}
     # replicas must be identical on every rank
     ref = multi.pos.clone()
     dist.broadcast(ref, 0)
@@ -40,6 +42,7 @@ for scheme in ("symmetric", "ordered"):
         out[scheme]["replicas_identical"] = bool(same.item())
 if rank == 0:
     print(json.dumps(out))
-    assert out["symmetric"]["bit_identical"] and out["symmetric"]["replicas_identical"]
+    for k in ("symmetric_peer", "symmetric_nccl"):
+        assert out[k]["bit_identical"] and out[k]["replicas_identical"], k
     assert out["ordered"]["max_abs_diff"] < 1e-3 and out["ordered"]["replicas_identical"]
 dist.destroy_process_group()
