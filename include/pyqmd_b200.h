@@ -247,6 +247,19 @@ int pyqmd_resolve_overlaps(const pyqmd_ensemble *e, const double *uniforms,
                            void *stream);
 
 /*
+ * Initial nucleon layout of every listed nucleus: Nucleus.initialize_particles, particles.py:62-124
+ * (shell-by-shell proton/neutron pairs, 20 candidate angles per nucleon, keep the one farthest from
+ * its nearest same-type neighbour).  Reads zn / offset / list / cap / id_base; writes pos (nucleus
+ * relative, FP32), vel = 0, is_proton and count = Z + N.  All listed nuclei must have the same
+ * nucleon count A <= cap; `shell_radii` = double[7], initial_radius * (i + 1) / 7 with
+ * initial_radius = 1.2 * A**(1/3) * 0.7 computed by the caller (:64-68).  `uniforms` (optional,
+ * device double[n_list][cap][21]): the draws of each placement in consumption order (radius factor,
+ * then 20 angles); otherwise Philox(seed).
+ */
+int pyqmd_ensemble_init_layout(const pyqmd_ensemble *e, const double *shell_radii,
+                               const double *uniforms, unsigned long long seed, void *stream);
+
+/*
  * Branch census of the pair law over every ordered pair of the listed nuclei
  * (nuclear_forces.py:257-291), for the algorithmic-FLOP accounting of the roofline; accumulates
  * into counts[8] (device): evaluated, skipped, hard core, core, attractive, tail, p-p, Pauli.

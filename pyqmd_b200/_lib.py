@@ -27,6 +27,7 @@ EXPORTS = (
     "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_integrate",
     "pyqmd_cloud_exchange_integrate",
     "pyqmd_ensemble_step", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
+    "pyqmd_ensemble_init_layout",
     "pyqmd_population_step",
 )
 
@@ -107,6 +108,8 @@ def lib():
     L.pyqmd_ensemble_step.argtypes = [C.POINTER(EnsembleDesc), i32, vp]
     L.pyqmd_resolve_overlaps.argtypes = [C.POINTER(EnsembleDesc), vp, i32, vp, vp]
     L.pyqmd_ensemble_census.argtypes = [C.POINTER(EnsembleDesc), vp, vp]
+    L.pyqmd_ensemble_init_layout.argtypes = [C.POINTER(EnsembleDesc), C.POINTER(C.c_double), vp,
+                                             C.c_uint64, vp]
     L.pyqmd_population_step.argtypes = [C.POINTER(PopulationDesc), i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -177,6 +177,49 @@ class NucleusEnsemble:
         return cls(zn, offsets, counts.to(torch.int32), pos, vel, isp, device=device,
                    id_base=id_base, **kw)
 
+    @classmethod
+    def from_device_layout(cls, isotopes, n_nuclei, *, device="cuda", id_base=0, layout_seed=0,
+                           layout_uniforms=None, **kw):
+        """Like ``from_templates`` but every nucleus gets its OWN layout, generated on the device by
+        the reference's placement algorithm (Nucleus.initialize_particles, particles.py:62-124;
+        pyqmd_ensemble_init_layout) instead of one of 64 reference-generated templates.
+        ``layout_uniforms``: optional {A: float64 [n_with_A, A, 21]} draws for parity tests."""
+        _lib.require_cuda()
+        dev = torch.device(device)
+        m = len(isotopes)
+        g = torch.arange(id_base, id_base + n_nuclei, device=dev, dtype=torch.int64)
+        iso = g % m
+        a_of = torch.tensor([z + n for z, n in isotopes], device=dev, dtype=torch.int64)
+        counts = a_of[iso]
+        offsets = torch.cumsum(counts, 0) - counts
+        total = int(counts.sum().item())
+        zn = torch.tensor([nuclides.zn_pack(z, n) for z, n in isotopes], device=dev,
+                          dtype=torch.int32)[iso]
+        pos = torch.zeros(total, 2, device=dev, dtype=torch.float32)
+        ens = cls(zn, offsets, counts.to(torch.int32), pos, torch.zeros_like(pos),
+                  torch.zeros(total, device=dev, dtype=torch.uint8), device=device, id_base=id_base,
+                  **kw)
+        ens.init_layout(layout_seed, layout_uniforms)
+        return ens
+
+    def init_layout(self, seed=0, uniforms=None):
+        """(Re)generate the initial layout of every nucleus on the device (particles.py:62-124)."""
+        lib = _lib.lib()
+        keep = []
+        for cap, lst, n_list in self.bins:
+            start = 1.2 * (cap ** (1 / 3)) * 0.7                  # particles.py:64-66
+            radii = (C.c_double * 7)(*[start * (i + 1) / 7 for i in range(7)])      # :68
+            u = None
+            if uniforms is not None:
+                u = torch.as_tensor(uniforms[cap], dtype=torch.float64).contiguous().to(self.device)
+                assert tuple(u.shape) == (n_list, cap, 21), (tuple(u.shape), (n_list, cap, 21))
+                keep.append(u)
+            d = self._desc(cap, lst, n_list, None)
+            _lib.check(lib.pyqmd_ensemble_init_layout(C.byref(d), radii, _lib.ptr(u), int(seed),
+                                                      _lib.current_stream()),
+                       "pyqmd_ensemble_init_layout")
+        torch.cuda.synchronize(self.device)
+
     # ---------------------------------------------------------------------------------------------
     def _desc(self, cap, lst, n_list, uniforms):
         d = _lib.EnsembleDesc()
