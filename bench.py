@@ -569,10 +569,11 @@ def bench_decay(args, K, W, rank, world, dev, dist, torch, sampler, hbm_peak, hb
         "ms_per_step": sec / K * 1e3, "scaling": "strong", "dtype": "f64",
         "config": {"workload": "C5 decay-only Monte Carlo, 1e8 C-14 / U-238 nuclei, Philox draws",
                    "substeps_per_step": sub, "parallelism": f"by-nucleus x{world}"},
-        "roofline": {"bound": "hbm", "achieved": n_mine * 40.0 * K / sec / 1e9, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": n_mine * 40.0 * K / sec / 1e9 / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": n_mine * 20.0 * K / sec / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": n_mine * 20.0 * K / sec / 1e9 / hbm_peak, "traffic": None,
                      "kernel": "population_kernel", "peak_source": hbm_src,
-                     "bytes_per_nucleus_launch": 40},
+                     "bytes_per_nucleus_launch": 20,
+                     "note": "read zn + half-life + p (20 B); written back only for decayed nuclei"},
     }
 
 

@@ -6,7 +6,8 @@
 // hit, by the (Z, N) / half-life part of handle_decay (nuclear_sim.py:213,288-289,353).
 //
 // One thread owns one nucleus for all n_steps sub-steps of a launch (state in registers,
-// HBM read once / written once).  Draws come from Philox4x32-10 keyed by (seed; global
+// HBM read once; written back only for nuclei that actually decayed -- 20 B per nucleus-launch
+// instead of 40).  Draws come from Philox4x32-10 keyed by (seed; global
 // nucleus id, step, slot) or, for the bit-exact parity path, from a caller-supplied array.
 // Per-step decay counts are reduced warp -> block -> one atomicAdd per block and column.
 #include "common.cuh"
@@ -31,10 +32,9 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
     }
     const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
     const uint64_t gid = (uint64_t)(P.id_base + i);
+    bool dirty = false;
 
     for (int s = 0; s < n_steps; ++s) {
-        if (threadIdx.x < PYQMD_COUNT_COLS) scount[threadIdx.x] = 0;
-        __syncthreads();
         const uint32_t step_abs = P.step0 + (uint32_t)s;
         bool fired = false;
         int mode = PYQMD_DECAY_NONE;
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
                 if (mode != PYQMD_DECAY_NONE) {             // :231-232
                     for (int wch = 0; wch < P.n_watch; ++wch)
                         if (P.watch_zn[wch] == zn) watch = wch;
+                    dirty = true;
                     zn = cur->opt_zn[k];                    // nuclear_sim.py:288-289
                     const pyqmd_nuclide_entry* nxt = lookup(P.table, zn);
                     double u3 = 0.0;
@@ -60,21 +61,22 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
             }
         }
         if (P.decided && ok) P.decided[(int64_t)s * P.n + i] = fired ? 1 : 0;
-        // warp-aggregated counters
+        // block-aggregated counters; one barrier per sub-step when nothing in the block decayed
         const bool counted = fired && mode != PYQMD_DECAY_NONE;
-        if (__any_sync(0xffffffffu, counted)) {
+        if (__syncthreads_or(counted)) {
+            if (threadIdx.x < PYQMD_COUNT_COLS) scount[threadIdx.x] = 0;
+            __syncthreads();
             if (counted) {
                 atomicAdd(&scount[mode], 1u);
                 if (watch >= 0) atomicAdd(&scount[8 + watch], 1u);
             }
+            __syncthreads();
+            if (threadIdx.x < PYQMD_COUNT_COLS && scount[threadIdx.x] && P.step_counts)
+                atomicAdd(P.step_counts + (int64_t)s * PYQMD_COUNT_COLS + threadIdx.x,
+                          (unsigned long long)scount[threadIdx.x]);
         }
-        __syncthreads();
-        if (threadIdx.x < PYQMD_COUNT_COLS && scount[threadIdx.x] && P.step_counts)
-            atomicAdd(P.step_counts + (int64_t)s * PYQMD_COUNT_COLS + threadIdx.x,
-                      (unsigned long long)scount[threadIdx.x]);
-        __syncthreads();
     }
-    if (ok) {
+    if (ok && dirty) {
         P.zn[i] = zn;
         P.half_life[i] = T;
         P.p_decay[i] = p;
