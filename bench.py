@@ -335,14 +335,27 @@ def main():
     line["gpu_launches"] = launches
 
     if not args.no_extras and args.workload == "ensemble":
-        # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection
-        for _ in range(3):
+        # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection, from a
+        # settled state (fresh layouts + 12 frames; the step-only state above has collapsed)
+        from pyqmd_b200.state import NucleusEnsemble
+        n_f = ens.n_nuclei
+        del ens
+        torch.cuda.empty_cache()
+        ens = NucleusEnsemble.from_templates((PB208,), n_f, device=dev, id_base=rank * n_f, decay=False)
+        for _ in range(12):
             ens.frame(4)
-        sec_f = timed_steps(lambda: ens.frame(4), 5, 1, dist, torch)
-        frame = {"ms_per_frame": sec_f / 5 * 1e3, "substeps_per_frame": 4,
-                 "nucleus_frames_per_s": float(tot_nuc.item()) * 5 / sec_f,
-                 "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 5 / sec_f,
-                 "note": "4 sub-steps + resolve_overlaps per frame, device resident"}
+        p0 = int(ens.push_count.item())
+        sec_f = timed_steps(lambda: ens.frame(4), 10, 1, dist, torch)
+        pushes = (int(ens.push_count.item()) - p0) / 11 / n_f
+        sec_s = timed_steps(lambda: ens.step(4), 10, 1, dist, torch)
+        census_f, flops_f = ens.census(range(0, n_f, max(1, n_f // 256)))
+        frame = {"ms_per_frame": sec_f / 10 * 1e3, "substeps_per_frame": 4,
+                 "ms_4_substeps_alone": sec_s / 10 * 1e3,
+                 "nucleus_frames_per_s": float(tot_nuc.item()) * 10 / sec_f,
+                 "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 10 / sec_f,
+                 "pushes_per_nucleus_frame": pushes, "flops_per_pair": flops_f,
+                 "branch_census": census_f,
+                 "note": "4 sub-steps + resolve_overlaps per frame, device resident, settled nuclei"}
         del ens
         torch.cuda.empty_cache()
         keep = ("metric", "unit", "value", "ms_per_step", "config", "roofline", "scaling",

@@ -27,6 +27,10 @@
 
 namespace pyqmd {
 
+#ifndef PYQMD_SYM_UNROLL
+#define PYQMD_SYM_UNROLL 1
+#endif
+constexpr int kSymUnroll = PYQMD_SYM_UNROLL;
 constexpr float kGhostI = -3.0e18f;   // padding i-nucleons: every term of the law is exactly 0
 constexpr float kGhostJ = 3.0e18f;    // padding j-nucleons (distinct from the i ghosts: d2 finite, > 0)
 constexpr int kWarps = kThreads / 32;
@@ -105,7 +109,7 @@ __device__ __forceinline__ void sweep_half(const float* __restrict__ sx, const f
         f32x2 nq2[kIPT];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) nq2[k] = pk1(-L.C * ti[k]);
-#pragma unroll 1
+#pragma unroll kSymUnroll
         for (int m = 0; m < 32; ++m) {
             const int q = (lane + m) & 31;
             const ulonglong2 X = x4[q], Y = y4[q];

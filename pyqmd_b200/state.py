@@ -383,7 +383,10 @@ class HostEnsembleRunner:
         self.n_chunks = len(self.chunks)
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, self.n_chunks))]
         self.h2d_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes + self.h_isp.nbytes)
-        self.d2h_bytes = int(self.h2d_bytes + self.h_count.nbytes + self.h_zn.nbytes)
+        # without decay the types / counts / (Z, N) cannot change: only positions and velocities
+        # come back, like the reference's download (nuclear_forces.py:227)
+        self.d2h_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes) + (
+            int(self.h_isp.nbytes + self.h_count.nbytes + self.h_zn.nbytes) if ens.decay else 0)
 
     def step(self, n_steps=1):
         ens = self.ens
@@ -400,9 +403,10 @@ class HostEnsembleRunner:
                     ens.launch(cap, lst_ptr, n_list, n_steps, st.cuda_stream)
                 self.h_pos[s0:s1].copy_(ens.pos[s0:s1], non_blocking=True)
                 self.h_vel[s0:s1].copy_(ens.vel[s0:s1], non_blocking=True)
-                self.h_isp[s0:s1].copy_(ens.is_proton[s0:s1], non_blocking=True)
-                self.h_count[a:b].copy_(ens.count[a:b], non_blocking=True)
-                self.h_zn[a:b].copy_(ens.zn[a:b], non_blocking=True)
+                if ens.decay:
+                    self.h_isp[s0:s1].copy_(ens.is_proton[s0:s1], non_blocking=True)
+                    self.h_count[a:b].copy_(ens.count[a:b], non_blocking=True)
+                    self.h_zn[a:b].copy_(ens.zn[a:b], non_blocking=True)
         for s in self.streams:
             cur.wait_stream(s)
         ens.step_index += n_steps
