@@ -129,6 +129,21 @@ def ncu_traffic(kernel):
         return None
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal affinity) BEFORE any pinned
+    host buffer is allocated, so that the e2e path's staging memory is first-touched on the GPU's
+    own NUMA node (8 ranks staging through one socket share its inter-socket links)."""
+    if os.environ.get("PYQMD_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -282,6 +297,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(physical_gpu_index(local_rank))
     dist = None
     if world > 1:
         import torch.distributed as dist
