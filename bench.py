@@ -558,7 +558,7 @@ def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, p
     return {
         "value": pairs * K / sec, "ms_per_step": sec / K * 1e3, "scaling": "strong",
         "config": {"workload": f"C4 single 2-D nucleon cloud N={n} (40% protons), all-pairs, "
-                               f"i-block sharded x{world}" + (" + NCCL position all-gather" if world > 1 else ""),
+                               f"i-block sharded x{world}",
                    "l2_policy": "per-step working set (positions 8N B) is L2 resident by design; "
                                 "compute bound", "dt_phys": 1 / 240,
                    "scheme": args.cloud_scheme, "exchange": cloud.exchange,
