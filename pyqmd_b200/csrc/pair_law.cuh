@@ -29,6 +29,8 @@ struct LawParams {
     float attrK;            // 1.25 * S           [278]
     float tailK;            // 0.15 * S           [281]
     float log2TailK;        // log2(0.15 * S)  (tail coefficient folded into the exponent)
+    float log2AttrK;        // log2(|1.25 * S|)
+    float sgnS;             // sign of S: carried by 1/(d+eps) so that the folded coefficients stay positive
     int   far_needs_clamp;  // 1 if |net| could reach 12 for d >= 9 with these strengths
 };
 
@@ -39,7 +41,9 @@ __host__ inline LawParams make_law_params(float S, float C, float P)
     p.coreK = 0.7f * S;
     p.attrK = 1.25f * S;
     p.tailK = 0.15f * S;
-    p.log2TailK = (p.tailK > 0.f) ? log2f(p.tailK) : -150.f;
+    p.log2TailK = (p.tailK != 0.f) ? log2f(fabsf(p.tailK)) : -150.f;
+    p.log2AttrK = (p.attrK != 0.f) ? log2f(fabsf(p.attrK)) : -150.f;
+    p.sgnS = (S < 0.f) ? -1.0f : 1.0f;
     // bound of |net| on d >= 9: tail <= tailK*exp(-1.8*9/7)/9.15, coulomb <= C/81.15
     double bound = fabs(0.15 * (double)S) * 0.09885 / 9.15 + fabs((double)C) / 81.15;
     p.far_needs_clamp = !(bound < 11.9) || !(S > 0.f);
@@ -114,17 +118,18 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
     float net = -60.0f * ov * mufu_sqrt(ov);
 
     // strong force: one reciprocal serves 1/(d+eps) and 1/(d2+eps) [275,278,281,285]
-    const float a = d + kEps;
+    const float a = fmaf(d, L.sgnS, L.sgnS * kEps);   // sgn(S) (d + eps)
     const float b = d2 + kEps;
     const float rab = mufu_rcp(a * b);
-    const float inv_a = rab * b;          // 1/(d+eps)
-    const float inv_b = rab * a;          // 1/(d2+eps)
+    const float inv_a = rab * b;          // sgn(S)/(d+eps)
+    const float inv_b = rab * a;          // 1/(d2+eps): the signs cancel
     const bool is_core = d2 < kCoreD * kCoreD;                    // [273]
     const bool is_attr = d2 < kAttrD * kAttrD;                    // [276]
+    // coefficient folded into the exponent: coef * exp(-k d) = 2^(log2 coef - k' d)
     const float kexp = is_attr ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f);
-    const float coef = is_attr ? L.attrK : L.tailK;
-    const float e = mufu_ex2(d * kexp);                           // exp(-d/7) or exp(-1.8 d/7)
-    const float strong = is_core ? (-L.coreK * inv_b) : (coef * e * inv_a);
+    const float lexp = is_attr ? L.log2AttrK : L.log2TailK;
+    const float e = mufu_ex2(fmaf(d, kexp, lexp));                // coef * exp(-d/7) or coef * exp(-1.8 d/7)
+    const float strong = is_core ? (-L.coreK * inv_b) : (e * inv_a);
     net += strong;
 
     // Coulomb between protons                                     [284-285]
@@ -140,10 +145,6 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
     return (d2 < kSkipD2) ? 0.0f : s;                             // [257]
 }
 
-#ifndef PYQMD_GEN_FOLD_COEF
-#define PYQMD_GEN_FOLD_COEF 1      // A/B on B200 (C2): +5 %
-#endif
-
 // Two general pairs at once: nucleons (i_a, i_b) of one thread against the same partner j, all
 // FMA-pipe arithmetic packed (f32x2), compares / selects / min-max / MUFU per element.
 //   dx, dy = (r_j - r_ia, r_j - r_ib);  tj2 = (t_j, t_j);  nq = (-C t_ia, -C t_ib).
@@ -151,6 +152,7 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
 struct GenConsts {
     f32x2 nInvHard, one, eps, negCoreK, n60, negP, kPauli;
     f32x2 kAttr, lAttr, kTail, lTail;      // 2^(k d + l) forms of the attractive / tail strong terms
+    f32x2 sgn, sgnEps;                     // sign of S and sgn * eps (see LawParams::sgnS)
 };
 
 __device__ __forceinline__ GenConsts make_gen_consts(const LawParams& L)
@@ -165,8 +167,10 @@ __device__ __forceinline__ GenConsts make_gen_consts(const LawParams& L)
     c.kPauli = pk1(-2.0f * kLog2e / kPauliD);
     c.kAttr = pk1(-kLog2e / 7.0f);
     c.kTail = pk1(-1.8f * kLog2e / 7.0f);
-    c.lAttr = pk1(L.attrK > 0.f ? log2f(L.attrK) : -150.f);
+    c.lAttr = pk1(L.log2AttrK);
     c.lTail = pk1(L.log2TailK);
+    c.sgn = pk1(L.sgnS);
+    c.sgnEps = pk1(L.sgnS * kEps);
     return c;
 }
 
@@ -186,7 +190,7 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     ovb = fmaxf(ovb, 0.f);
     const f32x2 hc = mul2(pk(ova, ovb), pk(mufu_sqrt(ova), mufu_sqrt(ovb)));
     // strong                                                        [273-281]
-    const f32x2 a = add2(d, c.eps), b = add2(d2, c.eps);
+    const f32x2 a = fma2(d, c.sgn, c.sgnEps), b = add2(d2, c.eps);   // a = sgn(S) (d + eps)
 #ifdef PYQMD_GEN_TWO_RCP
     float aa, ab, ba, bb;
     upk(a, aa, ab);
@@ -199,25 +203,15 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     const f32x2 inv_a = mul2(rab, b), inv_b = mul2(rab, a);
 #endif
     const bool attr_a = d2a < kAttrD * kAttrD, attr_b = d2b < kAttrD * kAttrD;
-#if PYQMD_GEN_FOLD_COEF
-    // coefficient folded into the exponent: coef * 2^(k d) = 2^(k d + log2 coef); both candidate
-    // arguments are computed packed, one select per element picks the branch
+    // coefficient folded into the exponent: |coef| * 2^(k d) = 2^(k d + log2 |coef|) (its sign rides on
+    // inv_a); both candidate arguments are computed packed, one select per element picks the branch
+    // (A/B on B200, C2: +5 % over select-k / select-coef / multiply)
     float xa, xb, ya, yb;
     upk(fma2(d, c.kAttr, c.lAttr), xa, xb);
     upk(fma2(d, c.kTail, c.lTail), ya, yb);
     const f32x2 e = pk(mufu_ex2(attr_a ? xa : ya), mufu_ex2(attr_b ? xb : yb));
     float sfa, sfb, sca, scb;
     upk(mul2(e, inv_a), sfa, sfb);
-#else
-    const f32x2 kexp = pk(attr_a ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f),
-                          attr_b ? (-kLog2e / 7.0f) : (-1.8f * kLog2e / 7.0f));
-    const f32x2 coef = pk(attr_a ? L.attrK : L.tailK, attr_b ? L.attrK : L.tailK);
-    float ea, eb;
-    upk(mul2(d, kexp), ea, eb);
-    const f32x2 e = pk(mufu_ex2(ea), mufu_ex2(eb));
-    float sfa, sfb, sca, scb;
-    upk(mul2(mul2(coef, e), inv_a), sfa, sfb);
-#endif
     upk(mul2(c.negCoreK, inv_b), sca, scb);
     const f32x2 strong = pk(d2a < kCoreD * kCoreD ? sca : sfa, d2b < kCoreD * kCoreD ? scb : sfb);
     f32x2 net = fma2(hc, c.n60, strong);

@@ -184,6 +184,22 @@ def test_symmetric_parts_sum_bit_identically():
 
 
 @pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("st", [(0.0, 30.0, 35.0), (-40.0, 30.0, 35.0)])
+def test_zero_and_negative_strong_strength(scheme, st):
+    """S <= 0 disables the far-field fast path (its folded log2 coefficient needs S > 0); the general
+    path carries the sign of S on 1/(d+eps)."""
+    from pyqmd_b200.state import NucleonCloud
+    n = 2500
+    pos, isp = make_cloud(n, seed=13)
+    cloud = NucleonCloud(pos, isp, keep_force=True, strengths=st, scheme=scheme)
+    cloud.step(1)
+    F = cloud.forces().cpu().numpy().astype(np.float64)
+    fx, fy = oracle_forces(pos, isp, 0, n, strengths=st)
+    amb = ambiguous_mask(pos, 0, n)
+    assert rel_l2(F, np.stack([fx, fy], 1), amb) <= FORCE_TOL
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
 def test_large_cloud_sampled_against_oracle(scheme):
     """N = 200,000: sorted, tile-classified fast path; 384 sampled nucleons against the oracle."""
     from pyqmd_b200.state import NucleonCloud

@@ -199,7 +199,9 @@ def test_non_default_strengths_and_dt():
     pos = rng.uniform(-12, 12, (n, 2)).astype(np.float32)
     vel = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
     isp = (rng.random(n) < 0.4).astype(np.uint8)
-    for S, C, P, dt in ((20.0, 3.0, 4.0, 1 / 60), (900.0, 300.0, 4.0, 1e-3), (150.0, 0.0, 0.0, 1 / 240)):
+    # the last two: S = 0 and a (non-physical) negative S -- the folded log2|coef| must keep its sign
+    for S, C, P, dt in ((20.0, 3.0, 4.0, 1 / 60), (900.0, 300.0, 4.0, 1e-3), (150.0, 0.0, 0.0, 1 / 240),
+                        (0.0, 30.0, 35.0, 1 / 240), (-40.0, 30.0, 35.0, 1 / 240)):
         ens = single_nucleus_ensemble(pos, vel, isp, dt_phys=dt, strengths=(S, C, P))
         ox, oy, _, _, fx, fy, amb = oracle_step(pos, vel, isp, dt, S, C, P)
         ens.step(1)
