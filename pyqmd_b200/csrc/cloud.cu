@@ -101,12 +101,7 @@ __global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_
 // + 2 special-function ops per pair): XU pipe 84 %, FMA pipe ~80 % busy -- both near saturation,
 // so this version (a) trims the FMA work to 12 ops per pair and (b) moves a fixed share of the
 // 2^x evaluations from the XU pipe to an FMA-pipe polynomial to balance the two pipes.
-// NPOLY of the 8 packed evaluations per (4 i x 4 j) inner iteration take the polynomial 2^x.
-#ifndef PYQMD_CLOUD_NPOLY
-#define PYQMD_CLOUD_NPOLY 0
-#endif
-
-template <int MODE, int NPOLY>
+template <int MODE>
 __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
                                                 const float* __restrict__ sy,
                                                 const float* __restrict__ st, int jmax,
@@ -135,21 +130,10 @@ __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
         if (MODE == 2) T = t4[jq];
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            // the polynomial evaluations are spread over the iteration (k = 0, 2, 1, 3 first halves)
-            constexpr int order[4] = {0, 2, 1, 3};
-            const bool pa = order[k] < NPOLY, pb = order[k] + 4 < NPOLY;
-            if (pa)
-                far_pair2<MODE, true>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull,
-                                      c, ax[k], ay[k]);
-            else
-                far_pair2<MODE, false>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull,
-                                       c, ax[k], ay[k]);
-            if (pb)
-                far_pair2<MODE, true>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull,
-                                      c, ax[k], ay[k]);
-            else
-                far_pair2<MODE, false>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull,
-                                       c, ax[k], ay[k]);
+            far_pair2<MODE>(X.x, Y.x, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.x) : 0ull, c, ax[k],
+                            ay[k]);
+            far_pair2<MODE>(X.y, Y.y, xi2[k], yi2[k], MODE == 2 ? mul2(nq2[k], T.y) : 0ull, c, ax[k],
+                            ay[k]);
         }
     }
 #pragma unroll
@@ -167,63 +151,6 @@ __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
             fx[k] = fmaf(dx, sc, fx[k]);
             fy[k] = fmaf(dy, sc, fy[k]);
         }
-    }
-}
-
-// Scalar twin of far_pair2 (same arithmetic, one pair per instruction), kept for A/B measurements of
-// packed vs scalar issue cost (PYQMD_CLOUD_SCALAR=1).
-template <int MODE>
-__device__ __forceinline__ void far_pair1(float xj, float yj, float xi, float yi, float cq,
-                                          const LawParams& L, float& fx, float& fy)
-{
-    const float dx = xj - xi, dy = yj - yi;
-    const float d2 = fmaf(dy, dy, dx * dx);
-    const float r = mufu_rsqrt(d2);
-    float arg = fmaf(d2 * r, -1.8f * kLog2e / 7.0f, L.log2TailK);
-    arg = fmaf(r, fmaf(r, kL2, kL1), arg);
-    const float e = mufu_ex2(arg);
-    const float r2 = r * r;
-    float s;
-    if (MODE == 0) {
-        s = e * r2;
-    } else {
-        const float g = fmaf(r2, fmaf(r2, kG2, kG1), 1.0f);
-        const float q = (MODE == 1) ? -L.C : cq;
-        s = r2 * fmaf(q * r, g, e);
-    }
-    fx = fmaf(dx, s, fx);
-    fy = fmaf(dy, s, fy);
-}
-
-template <int MODE>
-__device__ __forceinline__ void far_tile_scalar(const float* __restrict__ sx,
-                                                const float* __restrict__ sy,
-                                                const float* __restrict__ st, int jmax,
-                                                const float (&xi)[kIPT], const float (&yi)[kIPT],
-                                                const float (&qi)[kIPT], float (&fx)[kIPT],
-                                                float (&fy)[kIPT], const LawParams& L)
-{
-    const int quads = jmax >> 2;
-    const float4* x4 = reinterpret_cast<const float4*>(sx);
-    const float4* y4 = reinterpret_cast<const float4*>(sy);
-    const float4* t4 = reinterpret_cast<const float4*>(st);
-#pragma unroll 1
-    for (int jq = 0; jq < quads; ++jq) {
-        const float4 X = x4[jq], Y = y4[jq];
-        float4 T = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 2) T = t4[jq];
-#pragma unroll
-        for (int k = 0; k < kIPT; ++k) {
-            far_pair1<MODE>(X.x, Y.x, xi[k], yi[k], -qi[k] * T.x, L, fx[k], fy[k]);
-            far_pair1<MODE>(X.y, Y.y, xi[k], yi[k], -qi[k] * T.y, L, fx[k], fy[k]);
-            far_pair1<MODE>(X.z, Y.z, xi[k], yi[k], -qi[k] * T.z, L, fx[k], fy[k]);
-            far_pair1<MODE>(X.w, Y.w, xi[k], yi[k], -qi[k] * T.w, L, fx[k], fy[k]);
-        }
-    }
-    for (int j = quads << 2; j < jmax; ++j) {
-        const float ox = sx[j], oy = sy[j], tj = st[j];
-#pragma unroll
-        for (int k = 0; k < kIPT; ++k) far_pair1<MODE>(ox, oy, xi[k], yi[k], -qi[k] * tj, L, fx[k], fy[k]);
     }
 }
 
@@ -272,7 +199,7 @@ __device__ __forceinline__ void near_tile(const float* __restrict__ sx, const fl
 // float64 partial sums to partial[s][i - i0].  Splitting the j range keeps >= ~10 work units
 // per resident-block slot whatever N and the number of ranks are (wave quantisation was
 // costing 18 % at N = 1M on one GPU and > 50 % on eight).
-template <bool CLAMP, int NPOLY>
+template <bool CLAMP>
 __global__ void __launch_bounds__(kThreads, 2)
 cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict__ isp, int64_t n,
                    int64_t i0, int64_t i1, CloudWorkspace w, LawParams L, int far_enabled,
@@ -369,16 +296,9 @@ cloud_force_kernel(const float2* __restrict__ pos_in, const uint8_t* __restrict_
                 else if (mode == 1) far_tile_clamped<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
                 else far_tile_clamped<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
             } else {
-                if (NPOLY < 0) {
-                    if (mode == 0) far_tile_scalar<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                    else if (mode == 1) far_tile_scalar<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                    else far_tile_scalar<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                } else {
-                    constexpr int NP = NPOLY < 0 ? 0 : NPOLY;
-                    if (mode == 0) far_tile_packed<0, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                    else if (mode == 1) far_tile_packed<1, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                    else far_tile_packed<2, NP>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
-                }
+                if (mode == 0) far_tile_packed<0>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else if (mode == 1) far_tile_packed<1>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
+                else far_tile_packed<2>(sx, sy, st, jmax, xi, yi, qi, fx, fy, L);
             }
         } else {
             near_tile(sx, sy, st, jmax, xi, yi, ti, fx, fy, L);
@@ -503,25 +423,12 @@ extern "C" int pyqmd_cloud_step(const float* pos_in, float* pos_out, float* vel,
     PYQMD_REQUIRE((int64_t)n_seg * (i1 - i0) <= partial_entries(n), "workspace too small");
     const dim3 grid((unsigned)blocks, (unsigned)n_seg);
     const float2* pin = reinterpret_cast<const float2*>(pos_in);
-    // tuning knob (read once): share of polynomial 2^x evaluations, 0..4 of 8
-    static int npoly = -1;
-    if (npoly < 0) {
-        const char* env = getenv("PYQMD_CLOUD_NPOLY");
-        npoly = env ? atoi(env) : PYQMD_CLOUD_NPOLY;
-        if (npoly < 0 || npoly > 4) npoly = PYQMD_CLOUD_NPOLY;
-        if (getenv("PYQMD_CLOUD_SCALAR")) npoly = 9;
-    }
-#define PYQMD_LAUNCH_FORCE(CL, NP)                                                                  \
-    cloud_force_kernel<CL, NP><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,          \
-                                                          far_enabled, tiles_per_seg)
-    if (L.far_needs_clamp) PYQMD_LAUNCH_FORCE(true, 0);
-    else if (npoly == 0) PYQMD_LAUNCH_FORCE(false, 0);
-    else if (npoly == 1) PYQMD_LAUNCH_FORCE(false, 1);
-    else if (npoly == 2) PYQMD_LAUNCH_FORCE(false, 2);
-    else if (npoly == 3) PYQMD_LAUNCH_FORCE(false, 3);
-    else if (npoly == 9) PYQMD_LAUNCH_FORCE(false, -1);
-    else PYQMD_LAUNCH_FORCE(false, 4);
-#undef PYQMD_LAUNCH_FORCE
+    if (L.far_needs_clamp)
+        cloud_force_kernel<true><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
+                                                            far_enabled, tiles_per_seg);
+    else
+        cloud_force_kernel<false><<<grid, kThreads, 0, st>>>(pin, is_proton, n, i0, i1, w, L,
+                                                             far_enabled, tiles_per_seg);
     cloud_integrate_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, st>>>(
         pin, reinterpret_cast<float2*>(pos_out), reinterpret_cast<float2*>(vel),
         reinterpret_cast<float2*>(force), n, i0, i1, w, n_seg, dt);

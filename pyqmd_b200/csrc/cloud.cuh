@@ -59,20 +59,16 @@ inline CloudWorkspace carve(void* ws, int64_t n)
 
 struct FarConsts {
     f32x2 kexp, logA, l1, l2, g1, g2, one, negC;
-    f32x2 magic, p0, p1, p2, p3, p4, p5;
 };
 
 // Far-field approximations (all inside the 1e-5 budget, errors relative to the exact term):
 //   d/(d+eps) = 2^(-log2(1 + eps r)), r = 1/d <= 1/9: the correction is folded into the exponent of
 //       the tail, -log2(1 + eps r) ~= r (l1 + l2 r)           (minimax, 5.8e-8 relative in the term)
 //   1/(d2+eps) = r2 g(eps r2), g(w) ~= 1 + w (g1 + g2 w)      (minimax on w <= eps/81, 2e-10)
-//   2^f on [-0.5, 0.5] by a degree-5 minimax polynomial (7.5e-8 relative), used for a fixed share
-//       of the pairs so that the special-function and FMA pipes are both busy (see far_pair2)
 constexpr float kL1 = -0.2163957936310277f;      // in r (eps = 0.15 folded in)
 constexpr float kL2 = 0.01598281877193875f;
 constexpr float kG1 = -0.99999808f * kEps;       // in r2
 constexpr float kG2 = 0.99722842f * kEps * kEps;
-constexpr float kMagic = 12582912.0f;            // 1.5 * 2^23: round-to-nearest-integer by addition
 
 __device__ __forceinline__ FarConsts make_far_consts(const LawParams& L)
 {
@@ -85,45 +81,15 @@ __device__ __forceinline__ FarConsts make_far_consts(const LawParams& L)
     c.g2 = pk1(kG2);
     c.one = pk1(1.0f);
     c.negC = pk1(-L.C);
-    c.magic = pk1(kMagic);
-    c.p0 = pk1(1.00000007f);
-    c.p1 = pk1(0.69314697f);
-    c.p2 = pk1(0.2402212f);
-    c.p3 = pk1(0.05550713f);
-    c.p4 = pk1(0.00967554f);
-    c.p5 = pk1(0.00132765f);
     return c;
-}
-
-// 2^a for two arguments without the special-function unit: round to nearest integer by the magic
-// addition, degree-5 polynomial of the fraction on the FMA pipe (packed), exponent inserted with
-// one integer shift-add per element (ALU pipe).  Arguments below -126 are clamped: the result is
-// then < 1.2e-38, i.e. below anything that can change an FP32 force.
-__device__ __forceinline__ f32x2 exp2_poly2(f32x2 a, const FarConsts& c)
-{
-    float a0, a1;
-    upk(a, a0, a1);
-    a = pk(fmaxf(a0, -126.0f), fmaxf(a1, -126.0f));
-    const f32x2 t = add2(a, c.magic);
-    const f32x2 f = sub2(a, sub2(t, c.magic));
-    f32x2 p = fma2(c.p5, f, c.p4);
-    p = fma2(p, f, c.p3);
-    p = fma2(p, f, c.p2);
-    p = fma2(p, f, c.p1);
-    p = fma2(p, f, c.p0);
-    float p0, p1, t0, t1;
-    upk(p, p0, p1);
-    upk(t, t0, t1);
-    const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-    const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-    return pk(e0, e1);
 }
 
 // Two far pairs (one i, two j) in packed form.
 //   s = net / d,  net = 0.15 S exp(-1.8 d/7)/(d + eps) - [pp] C/(d2 + eps)      [281,285]
 // FMA-pipe operations per pair: 12 (MODE 0), 15 (MODE 1), 17 (MODE 2); special-function ops: 2
-// (rsqrt, ex2), or 1 + 8 more FMA-pipe ops when POLY.
-template <int MODE, bool POLY>
+// (rsqrt, ex2).  A degree-5 polynomial 2^x on the FMA pipe for a share of the pairs was measured
+// (r01e+) and rejected: every share was slower, the FMA pipe is as busy as the XU pipe.
+template <int MODE>
 __device__ __forceinline__ void far_pair2(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
                                           const FarConsts& c, f32x2& fx, f32x2& fy)
 {
@@ -134,13 +100,8 @@ __device__ __forceinline__ void far_pair2(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi
     const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
     f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
     arg = fma2(r, fma2(r, c.l2, c.l1), arg);
-    f32x2 e;
-    if (POLY) {
-        e = exp2_poly2(arg, c);
-    } else {
-        upk(arg, a0, a1);
-        e = pk(mufu_ex2(a0), mufu_ex2(a1));
-    }
+    upk(arg, a0, a1);
+    const f32x2 e = pk(mufu_ex2(a0), mufu_ex2(a1));
     const f32x2 r2 = mul2(r, r);
     f32x2 s;
     if (MODE == 0) {

@@ -435,12 +435,12 @@ extern "C" int pyqmd_cloud_pair_forces(const float* pos, const uint8_t* is_proto
     sp.n_parts = n_parts;
     sp.far_enabled = (strong > 0.f && !L.far_needs_clamp) ? 1 : 0;
     sp.scale = ldexpf(1.0f, scale_log2_for(n));
-    // ~24 units per resident-block slot of this part (148 SMs x 2), 4..64 tiles each
+    // ~24 units per resident-block slot of this part (148 SMs x 2), 4..64 tiles each (a sweep of
+    // 8..128 tiles per unit on B200 at N = 1M changed the step time by < 0.8 %)
     const double tiles_total = 0.5 * (double)sp.nb * (double)nt / n_parts;
     int tpu = (int)(tiles_total / (296.0 * 24.0));
     if (tpu > 64) tpu = 64;
     if (tpu < 4) tpu = 4;
-    if (const char* env = getenv("PYQMD_CLOUD_TPU")) { const int v = atoi(env); if (v >= 1) tpu = v; }
     sp.tiles_per_unit = tpu;
     const int rows_mine = (sp.nb + n_parts - 1) / n_parts;
     const int units_max = (int)((nt + tpu - 1) / tpu);

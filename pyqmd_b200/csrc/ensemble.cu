@@ -381,7 +381,7 @@ __device__ __forceinline__ void publish_pair_sums(float4* wsum, int capT, int g,
 #ifndef PYQMD_ENS_MINBLOCKS
 #define PYQMD_ENS_MINBLOCKS 4      // A/B on B200: 2 -> 1.01e12, 3 -> 1.07e12, 4 -> 1.12e12, 5 -> spills
 #endif
-template <int MAXT, bool SCALAR = false>
+template <int MAXT>
 __global__ void __launch_bounds__(MAXT, PYQMD_ENS_MINBLOCKS) ensemble_pair_kernel(const pyqmd_ensemble e,
                                                               const LawParams L, const int n_steps,
                                                               const int G, const int capT)
@@ -548,26 +548,9 @@ __global__ void __launch_bounds__(MAXT, PYQMD_ENS_MINBLOCKS) ensemble_pair_kerne
             const f32x2 nq2 = pk(-L.C * t0, -L.C * t1);
             f32x2 fx2 = pk(0.f, 0.f), fy2 = pk(0.f, 0.f);
             const int capT_ = capT;
-            float sfx0 = 0.f, sfy0 = 0.f, sfx1 = 0.f, sfy1 = 0.f;
             auto visit = [&](int u, int par) {              // partner slot 2u + par
                 const ulonglong2 o = Ag[par * capS + u];
                 const float2 tt = Tg[par * capS + u];
-                if (SCALAR) {                               // A/B variant: one pair per instruction
-                    float ox, oy, dummy;
-                    upk(o.x, ox, dummy);
-                    upk(o.y, oy, dummy);
-                    const float dxa = ox - x0, dya = oy - y0, dxb = ox - x1, dyb = oy - y1;
-                    const float sa = pair_general(dxa, dya, t0, tt.x, L);
-                    const float sb = pair_general(dxb, dyb, t1, tt.x, L);
-                    const float pxa = dxa * sa, pya = dya * sa, pxb = dxb * sb, pyb = dyb * sb;
-                    sfx0 += pxa; sfy0 += pya; sfx1 += pxb; sfy1 += pyb;
-                    const unsigned ur = min((unsigned)u, (unsigned)(u - m));
-                    float2 r = row[par * capT_ + ur];
-                    r.x -= pxa + pxb;
-                    r.y -= pya + pyb;
-                    row[par * capT_ + ur] = r;
-                    return;
-                }
                 const f32x2 dx2 = sub2(o.x, xi2), dy2 = sub2(o.y, yi2);
                 const f32x2 sc2 = pair_general2(dx2, dy2, t0, t1, tt.x, pk(tt.x, tt.y), nq2, gc, L);
                 const f32x2 px2 = mul2(dx2, sc2), py2 = mul2(dy2, sc2);
@@ -595,7 +578,6 @@ __global__ void __launch_bounds__(MAXT, PYQMD_ENS_MINBLOCKS) ensemble_pair_kerne
             }
             upk(fx2, f0x, f1x);
             upk(fy2, f0y, f1y);
-            if (SCALAR) { f0x = sfx0; f0y = sfy0; f1x = sfx1; f1y = sfy1; }
             {                                               // the thread's own pair (2t, 2t+1)
                 const float dx = x1 - x0, dy = y1 - y0;
                 const float sc = pair_general(dx, dy, t0, t1, L);
@@ -718,19 +700,7 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
                 attr_set = true;
             }
             // blocks of <= 224 threads: 4 blocks / SM at 72 registers per thread
-            static int scalar_ab = -1;
-            if (scalar_ab < 0) scalar_ab = getenv("PYQMD_ENS_SCALAR") ? 1 : 0;
-            if (scalar_ab) {
-                static bool attr2 = false;
-                if (!attr2) {
-                    PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<256, true>,
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          200 * 1024));
-                    attr2 = true;
-                }
-                ensemble_pair_kernel<256, true><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
-                    d, Lp, n_steps, Gp, capT);
-            } else if (Tp <= 224)
+            if (Tp <= 224)
                 ensemble_pair_kernel<224><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
                     d, Lp, n_steps, Gp, capT);
             else
