@@ -482,6 +482,10 @@ def bench_ensemble(args, workload, K, W, rank, world, dev, dist, torch, sampler,
         res["e2e"] = {"value": float(tot_pairs.item()) * k2 / sec_e2e, "unit": "pairs/s",
                       "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
                       "chunks": runner.n_chunks}
+        # for information: one host round trip per app frame (4 sub-steps, nuclear_sim.py:153) instead of
+        # one per sub-step -- what NuclearForces.step(particles, dt, n) offers over the reference's call
+        sec_e2e4 = timed_steps(lambda: runner.step(4 * args.substeps), max(3, k2 // 4), 1, dist, torch)
+        res["e2e"]["value_4_substeps_per_call"] = (float(tot_pairs.item()) * 4 * max(3, k2 // 4) / sec_e2e4)
         del runner
     return res, ens, tot_nuc, tot_pairs
 
