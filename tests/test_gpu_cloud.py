@@ -230,3 +230,40 @@ def test_multi_step_cloud_teacher_forced(scheme):
         fx, fy = oracle_forces(p0, isp, 0, n)
         amb = ambiguous_mask(p0, 0, n)
         assert rel_l2(cloud.force.cpu().numpy().astype(np.float64), np.stack([fx, fy], 1), amb) <= FORCE_TOL
+
+
+def test_full_size_cloud_1M_properties():
+    """Config C4 at full size (N = 10^6, 40 % protons): sampled nucleons against the oracle, Newton's
+    third law over the whole cloud, and the symmetric scheme against the ordered kernel on a block."""
+    from pyqmd_b200 import _lib
+    from pyqmd_b200.state import NucleonCloud
+    n = 1_000_000
+    pos, isp = make_cloud(n)
+    cloud = NucleonCloud(pos, isp, keep_force=True)
+    p_sorted = cloud.pos[:n].cpu().numpy().copy()
+    t_sorted = cloud.is_proton.cpu().numpy().copy()
+    lib = _lib.lib()
+    acc = torch.zeros(n, 2, dtype=torch.int64, device="cuda")
+    _lib.check(lib.pyqmd_cloud_pair_forces(cloud.pos.data_ptr(), cloud.is_proton.data_ptr(), n, 0, 1,
+                                           150.0, 30.0, 35.0, acc.data_ptr(), cloud.workspace.data_ptr(),
+                                           _lib.current_stream()), "pair_forces")
+    torch.cuda.synchronize()
+    assert acc.sum(0).abs().max().item() <= 1e-6 * acc.abs().sum().item()      # pair forces cancel
+    cloud.step(1)
+    F = cloud.force.cpu().numpy().astype(np.float64)                           # sorted order
+    x, y = p_sorted[:, 0].astype(np.float64), p_sorted[:, 1].astype(np.float64)
+    c = (float(x.mean()), float(y.mean()))
+    for i0 in (0, 399_900, 654_321, n - 64):                                   # p block, p/n border, n block
+        fx, fy = orc.cloud_forces(x, y, t_sorted, i0, i0 + 64, center=c)
+        amb = ambiguous_mask(p_sorted, i0, i0 + 64)
+        assert rel_l2(F[i0:i0 + 64], np.stack([fx, fy], 1), amb) <= FORCE_TOL, i0
+    # ordered kernel on one 4096-nucleon block of the same (sorted) cloud
+    o = NucleonCloud(p_sorted, t_sorted, keep_force=True, scheme="ordered", sort=False)
+    o.i0, o.i1 = 500_000, 504_096
+    o.step(1)
+    Fo = o.force[o.i0:o.i1].cpu().numpy().astype(np.float64)
+    assert rel_l2(F[o.i0:o.i1], Fo) <= 2e-6
+    # one step from rest: x' = x + 0.85 F dt^2
+    got = cloud.pos[:n].cpu().numpy().astype(np.float64)
+    want = p_sorted.astype(np.float64) + 0.85 * F * cloud.dt ** 2
+    assert np.abs(got - want).max() / extent_of(p_sorted) <= POS_TOL

@@ -101,15 +101,15 @@ def test_philox_stream_matches_oracle_and_is_shard_invariant():
 
 
 def test_half_life_statistics_config5():
-    """Config C5 (scaled to 2x10^7 nuclei): survivors per step follow the reference's effective
+    """Config C5 at full size (10^8 nuclei, half C-14, half U-238): survivors per step follow the reference's effective
     law N0 (1-p)^k (4 sigma), which sits 9.3e-5 (relative rate) off the analytic 0.5^(t/T)
     because the reference uses 0.693 for ln 2 (particles.py:140)."""
     from pyqmd_b200.state import DecayPopulation
-    n = 20_000_000
+    n = 100_000_000
     znv = torch.full((n,), zn(*C14), dtype=torch.int32)
     znv[n // 2:] = zn(*U238)
     Tc, Tu = dor.half_life(*C14)[0], dor.half_life(*U238)[0]
-    steps = 200
+    steps = 100
     for (T, watch_col) in ((Tc, 8), (Tu, 9)):
         dt = T / 1000.0
         pop = DecayPopulation(znv, dt_decay=dt, seed=99, watch=(C14, U238))
@@ -266,3 +266,49 @@ def test_mixed_ensemble_decay_statistics_and_sharding():
         o, c = int(a.offsets[k]), int(a.count[k])
         ow = int(whole.offsets[k])
         assert torch.equal(a.pos[o:o + c], whole.pos[ow:ow + c])
+
+
+def test_full_size_mixed_ensemble_1M_properties():
+    """Config C3 at full size (10^6 nuclei over the nine preset isotopes, decay on): sampled nuclei
+    against the oracle for the first sub-step, then bookkeeping invariants after a few sub-steps
+    with a decay probability large enough to fire thousands of events."""
+    from pyqmd_b200.state import NucleusEnsemble, README_ISOTOPES
+    from pyqmd_b200.types import DecayType
+    n = 1_000_000
+    T_c14 = dor.half_life(*C14)[0]
+    ens = NucleusEnsemble.from_templates(README_ISOTOPES, n, dt_decay=T_c14 * 2e-3, seed=77,
+                                         event_capacity=1 << 16)
+    assert ens.pairs_per_step() == sum((z + m) * (z + m - 1) for z, m in README_ISOTOPES) * (n // 9) + \
+        sum((z + m) * (z + m - 1) for z, m in README_ISOTOPES[: n % 9])
+    off, cnt0 = ens.offsets.cpu().numpy(), ens.count.cpu().numpy().copy()
+    zn0 = ens.zn.cpu().numpy().copy()
+    sample = [5, 6, 7, 8, 500_003, 500_004, 999_997, 999_998, 999_999]      # heavy and light isotopes
+    before = {k: (ens.pos[off[k]:off[k] + cnt0[k]].cpu().numpy().copy(),
+                  ens.is_proton[off[k]:off[k] + cnt0[k]].cpu().numpy().copy()) for k in sample}
+    ens.step(1)
+    zn1 = ens.zn.cpu().numpy()
+    for k in sample:
+        if zn1[k] != zn0[k]:
+            continue                                        # decayed in this sub-step: covered elsewhere
+        p0, isp = before[k]
+        ox, oy, _, _, _, _, amb = oracle_step(p0, np.zeros_like(p0), isp, ens.dt_phys)
+        got = ens.pos[off[k]:off[k] + cnt0[k]].cpu().numpy()
+        assert pos_error(p0, got, ox, oy, amb) <= POS_TOL, k
+    ens.step(4)
+    assert torch.isfinite(ens.pos).all()
+    events = int(ens.event_count.item())
+    mc = ens.mode_counts.cpu().numpy()
+    assert events == int(mc.sum()) and events > 500
+    # C-14 (beta-minus -> N-14, stable) decays at this dt; U-238 (p ~ 2e-9 per sub-step) practically never
+    changed = np.nonzero(ens.zn.cpu().numpy() != zn0)[0]
+    assert len(changed) == events and np.isin(changed % 9, (3, 8)).all()
+    assert mc[DecayType.BETA_MINUS.value] >= events - 2
+    c14 = np.arange(3, n, 9)
+    assert np.array_equal(ens.count.cpu().numpy()[c14], cnt0[c14])  # beta decay keeps the nucleon count
+    isp = ens.is_proton.cpu().numpy()
+    z_now = np.array([isp[off[k]:off[k] + 14].sum() for k in changed[changed % 9 == 3][:200]])
+    assert (z_now == 7).all()                                       # one neutron became a proton
+    p = orc.decay_probability(T_c14, T_c14 * 2e-3)
+    n_c14 = len(range(3, n, 9))
+    expect = n_c14 * (1 - (1 - p) ** 5)
+    assert abs(events - expect) < 5 * np.sqrt(expect) + 1
