@@ -54,6 +54,33 @@ def sym_row_work(b: int, n: int) -> int:
     return max(nt - 4 * b, 0)
 
 
+def sym_row_tiles(b: int, n: int):
+    """(diagonal tiles, off-diagonal tiles) of row ``b``: the row's own 4 tiles are evaluated as
+    ordered pairs without reaction, every later tile once per unordered pair with the reaction
+    added to the j side (csrc/cloud_sym.cu)."""
+    nt = (n + 255) // 256
+    first = 4 * b
+    return list(range(first, min(first + 4, nt))), list(range(first + 4, nt))
+
+
+def reduce_scatter_forces(acc: torch.Tensor, mine: torch.Tensor, rank: int, world: int, group=None):
+    """Exact sum over ranks of the int64 fixed-point force accumulators; rank r receives the rows
+    [r*chunk, (r+1)*chunk) in ``mine``.  NCCL: reduce_scatter_tensor; backends without it (gloo in
+    the CPU test-suite): all_reduce + slice."""
+    import torch.distributed as dist
+    chunk = mine.shape[0]
+    if world == 1:
+        mine.copy_(acc[:chunk])
+        return mine
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(mine, acc, op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = acc.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        mine.copy_(tmp[rank * chunk:(rank + 1) * chunk])
+    return mine
+
+
 def allgather_positions(replica: torch.Tensor, rank: int, world: int, chunk: int, group=None):
     """In-place all-gather of the rows each rank owns in its [chunk * world, 2] replica."""
     if world == 1:

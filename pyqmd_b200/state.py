@@ -77,7 +77,8 @@ def initial_half_lives(zn: np.ndarray, dt_decay: float, rng: np.random.Generator
     return T, p
 
 
-from .sharding import allgather_positions, cloud_chunk, shard_range  # noqa: E402,F401
+from .sharding import (allgather_positions, cloud_chunk, reduce_scatter_forces,  # noqa: E402,F401
+                       shard_range)
 
 
 # =================================================================================================
@@ -547,8 +548,7 @@ class NucleonCloud:
                     self.steps_done += 1
                     continue
                 if self.world > 1:
-                    dist.reduce_scatter_tensor(self.acc_mine, self.acc, op=dist.ReduceOp.SUM,
-                                               group=self.group)
+                    reduce_scatter_forces(self.acc, self.acc_mine, self.rank, self.world, self.group)
                     self.acc.zero_()
                 if self.i1 > self.i0:
                     _lib.check(lib.pyqmd_cloud_integrate(

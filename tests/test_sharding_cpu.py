@@ -106,3 +106,62 @@ def test_symmetric_cloud_rows_partition_and_balance():
             if n >= 200_000:
                 work = [sum(sym_row_work(b, n) for b in rows) for rows in owned]
                 assert max(work) <= 1.02 * (sum(work) / parts), (n, parts, work)
+
+
+def _pair(i, j):
+    """An antisymmetric integer 'pair force' (stands in for the fixed-point force of nucleon j on i)."""
+    h = (np.minimum(i, j) * 2654435761 + np.maximum(i, j) * 40503) % 2001 - 1000
+    return np.where(i < j, h, -h) * (i != j)
+
+
+def _sym_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = sharding.cloud_chunk(n, world)
+        acc = torch.zeros(chunk * world, 2, dtype=torch.int64)
+        a = acc.numpy()
+        # this rank's share of the symmetric scheme, restated on the host (csrc/cloud_sym.cu):
+        # row b = i in [1024 b, 1024 b + 1024); diagonal tiles ordered, later tiles with reaction
+        for b in sharding.sym_rows_of(rank, world, n):
+            i = np.arange(1024 * b, min(1024 * b + 1024, n))
+            diag, later = sharding.sym_row_tiles(b, n)
+            for t in diag:
+                j = np.arange(256 * t, min(256 * t + 256, n))
+                f = _pair(i[:, None], j[None, :])
+                a[i, 0] += f.sum(1)
+            for t in later:
+                j = np.arange(256 * t, min(256 * t + 256, n))
+                f = _pair(i[:, None], j[None, :])
+                a[i, 0] += f.sum(1)
+                a[j, 0] -= f.sum(0)
+        a[:, 1] = 3 * a[:, 0]
+        mine = torch.zeros(chunk, 2, dtype=torch.int64)
+        sharding.reduce_scatter_forces(acc, mine, rank, world)
+        lo, hi = sharding.shard_range(n, rank, world)
+        idx = np.arange(n)
+        want = _pair(idx[lo:hi, None], idx[None, :]).sum(1)
+        ok = np.array_equal(mine.numpy()[: hi - lo, 0], want) and \
+            np.array_equal(mine.numpy()[: hi - lo, 1], 3 * want)
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [700, 2500, 4096 + 300])
+def test_symmetric_cloud_force_exchange_world2(n):
+    """Rows dealt to two ranks + exact int64 reduce-scatter reproduce the all-pairs sums: every
+    unordered pair is counted exactly once across the ranks (gloo, no GPU)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sym_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
