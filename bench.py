@@ -129,21 +129,6 @@ def ncu_traffic(kernel):
         return None
 
 
-def bind_to_gpu_numa_node(index):
-    """Pin this process to the CPUs closest to its GPU (NVML's ideal affinity) BEFORE any pinned
-    host buffer is allocated, so that the e2e path's staging memory is first-touched on the GPU's
-    own NUMA node (8 ranks staging through one socket share its inter-socket links)."""
-    if os.environ.get("PYQMD_NO_AFFINITY"):
-        return None
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
-        return sorted(os.sched_getaffinity(0))
-    except Exception:
-        return None
-
-
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -297,7 +282,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    bind_to_gpu_numa_node(physical_gpu_index(local_rank))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -392,6 +376,26 @@ def main():
         torch.cuda.empty_cache()
         if rank == 0:
             also["c1"] = bench_c1(dev, torch)
+        if rank == 0 and world == 1:
+            # the reference's CPU path (C port, all host threads) beside each config
+            from oracle import oracle as orc
+            threads = orc.max_threads()
+            v, dt_s = cpu_cloud_sample(65536, 64 * threads, threads)
+            also["cloud"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                             "sample": f"{64 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
+            v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 2, threads)
+            also["mixed"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "nucleus_steps_per_s": ns,
+                                             "cores": threads, "kind": "port",
+                                             "sample": f"{9 * 32 * threads} nuclei x 2 sub-steps, {dt_s:.1f} s"}
+            n_d = 4_000_000 * threads
+            Tn = np.full(n_d, 180825048000.0)
+            un = np.random.default_rng(1).random(n_d)
+            t0 = time.perf_counter()
+            orc.decay_decisions(Tn, 180825048000.0 * 1e-3, un, n_threads=threads)
+            dt_s = time.perf_counter() - t0
+            also["decay"]["cpu_baseline"] = {"value": n_d / dt_s, "unit": "nucleus-steps/s", "cores": threads,
+                                             "kind": "port",
+                                             "sample": f"{n_d} should_decay decisions with supplied uniforms, {dt_s:.2f} s"}
         line["also"] = also
 
     if rank == 0 and world == 1:

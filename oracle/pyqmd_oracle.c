@@ -209,7 +209,7 @@ int64_t orc_ensemble_force_steps(int64_t n_nuclei, const int64_t *offsets, const
 {
     int64_t pairs = 0;
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());   /* 0 = all host cores */
 #endif
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : pairs)
     for (int64_t k = 0; k < n_nuclei; ++k) {
@@ -234,7 +234,7 @@ void orc_cloud_forces(int64_t n, const double *x, const double *y, const uint8_t
 {
     double nuclear_radius = 1.2 * pow((double)n, 1.0 / 3.0) * 2.0;
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());   /* 0 = all host cores */
 #endif
 #pragma omp parallel for schedule(static)
     for (int64_t i = i0; i < i1; ++i) {
@@ -349,7 +349,7 @@ int64_t orc_decay_decisions(int64_t n, const double *T, double dt, const double 
 {
     int64_t fired = 0;
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());   /* 0 = all host cores */
 #endif
 #pragma omp parallel for schedule(static) reduction(+ : fired)
     for (int64_t k = 0; k < n; ++k) {
@@ -420,7 +420,7 @@ void orc_philox_uniforms(uint64_t seed, uint64_t id0, int64_t n, uint32_t step, 
 int orc_max_threads(void)
 {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();      /* not omp_get_max_threads(): that follows the last omp_set_num_threads */
 #else
     return 1;
 #endif
