@@ -163,6 +163,7 @@ def cpu_ensemble_sample(isotopes, n_nuclei, n_steps, threads):
 
 def cpu_cloud_sample(n, n_i, threads, seed=1234):
     from oracle import oracle as orc
+    n_i = min(n_i, n)
     pos, isp = make_cloud(n, seed)
     x, y = pos[:, 0].astype(np.float64), pos[:, 1].astype(np.float64)
     t0 = time.perf_counter()
@@ -380,13 +381,13 @@ def main():
             # the reference's CPU path (C port, all host threads) beside each config
             from oracle import oracle as orc
             threads = orc.max_threads()
-            v, dt_s = cpu_cloud_sample(65536, 64 * threads, threads)
+            v, dt_s = cpu_cloud_sample(65536, 1024 * threads, threads)
             also["cloud"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                             "sample": f"{64 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
-            v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 2, threads)
+                                             "sample": f"{1024 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
+            v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 10, threads)
             also["mixed"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "nucleus_steps_per_s": ns,
                                              "cores": threads, "kind": "port",
-                                             "sample": f"{9 * 32 * threads} nuclei x 2 sub-steps, {dt_s:.1f} s"}
+                                             "sample": f"{9 * 32 * threads} nuclei x 10 sub-steps, {dt_s:.1f} s"}
             n_d = 4_000_000 * threads
             Tn = np.full(n_d, 180825048000.0)
             un = np.random.default_rng(1).random(n_d)
@@ -402,17 +403,17 @@ def main():
         from oracle import oracle as orc
         threads = orc.max_threads()
         if args.workload == "cloud":
-            v, dt = cpu_cloud_sample(65536, 64 * threads, threads)
+            v, dt = cpu_cloud_sample(65536, 4096 * threads, threads)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "sample": f"{64 * threads} i-nucleons of a 65,536-nucleon cloud, "
+                                    "sample": f"{min(4096 * threads, 65536)} i-nucleons of a 65,536-nucleon cloud, "
                                               f"{dt:.1f} s"}
         elif args.workload in ("ensemble", "mixed"):
             isotopes = (PB208,) if args.workload == "ensemble" else README_ISOTOPES
             n_s = 256 * threads
-            v, ns, dt = cpu_ensemble_sample(isotopes, n_s, 2, threads)
+            v, ns, dt = cpu_ensemble_sample(isotopes, n_s, 30, threads)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                                     "nucleus_steps_per_s": ns,
-                                    "sample": f"{n_s} nuclei x 2 sub-steps of the same workload, "
+                                    "sample": f"{n_s} nuclei x 30 sub-steps of the same workload, "
                                               f"{dt:.1f} s, OpenMP over nuclei"}
     if rank == 0:
         print(json.dumps(line))
