@@ -123,6 +123,7 @@ class HeadlessSimulation:
                                                        seed=seed, origin=org, rotate=rotate,
                                                        dt_decay=1.0 / 240.0)
         self._events_seen = 0
+        self.events_dropped = 0
         # free (emitted) particles, SoA on the host: few and short-lived
         self.free = {k: np.zeros(0) for k in ("x", "y", "vx", "vy", "age", "lifetime")}
         self.free["type"] = np.zeros(0, np.int32)
@@ -174,12 +175,15 @@ class HeadlessSimulation:
         for d in DecayType:
             if d != DecayType.NONE:
                 self.decay_counts[d.name] = int(mc[d.value])
-        if total == self._events_seen:
+        if total == 0:
             return
-        ev = ens.events()
-        ev = ev[np.argsort(ev["step"], kind="stable")]
-        new = ev[self._events_seen:] if len(ev) >= total else ev[-(total - self._events_seen):]
-        self._events_seen = total
+        # the device log holds this frame's events only: it is drained (cursor reset) every frame, so
+        # long runs never overflow it; events beyond its capacity within ONE frame are counted in
+        # decay_counts but get no free particle
+        new = ens.events()                       # sorted by (step, nucleus)
+        self.events_dropped += max(0, total - len(new))
+        ens.event_count.zero_()
+        self._events_seen += total
         new = new[new["ptype"] >= 0]
         if len(new) == 0:
             return
