@@ -85,6 +85,34 @@ def cosmetic_speed_lifetime(ptype, vx, vy, time_scale, substeps_used, physics_dt
     return vx, vy, lifetime
 
 
+def cosmetic_speed_lifetime_array(ptype, vx, vy, time_scale, substeps_used, physics_dt):
+    """Vectorised ``cosmetic_speed_lifetime`` (same IEEE operations in the same order, so the
+    results are bit-identical) for the thousands of events a large ensemble emits per frame."""
+    ptype = np.asarray(ptype)
+    vx, vy = np.asarray(vx, np.float64).copy(), np.asarray(vy, np.float64).copy()
+    base_speed = np.full(ptype.shape, 40.0)
+    base_speed[ptype == ParticleType.ALPHA.value] = 30.0
+    base_speed[ptype == ParticleType.GAMMA.value] = 60.0
+    base_speed[(ptype == ParticleType.ELECTRON.value) | (ptype == ParticleType.POSITRON.value)] = 50.0
+    # the reference squares with ``**`` (libm pow, not guaranteed to round like a product): keep that
+    # one operation in Python so every bit matches; sqrt / divide / multiply are IEEE in numpy too
+    mag = np.sqrt(np.array([a ** 2 + b ** 2 for a, b in zip(vx.tolist(), vy.tolist())], np.float64))
+    ok = mag > 0.001
+    safe = np.where(ok, mag, 1.0)
+    vx = np.where(ok, (vx / safe) * base_speed, vx)
+    vy = np.where(ok, (vy / safe) * base_speed, vy)
+    if time_scale > 1.0:
+        _, _, life = cosmetic_speed_lifetime(ParticleType.ALPHA.value, 1.0, 0.0, time_scale,
+                                             substeps_used, physics_dt)
+        lifetime = np.full(ptype.shape, life)
+    else:
+        default = np.full(ptype.shape, float("inf"))
+        for k, v in _DEFAULT_LIFETIME.items():
+            default[ptype == k] = v
+        lifetime = np.maximum(default, 5.0 * max(1.0, substeps_used / 5.0))
+    return vx, vy, lifetime
+
+
 def animate(ptype, x, y, vx, vy, age, lifetime, dt, age_dt, time_scale, substeps_used):
     """One update_particle call (nuclear_sim.py:178-210) on arrays; returns (x, y, age, alive)."""
     ptype = np.asarray(ptype)
@@ -187,14 +215,11 @@ class HeadlessSimulation:
         new = new[new["ptype"] >= 0]
         if len(new) == 0:
             return
-        vx, vy, life = [], [], []
-        for e in new:
-            a, b, c = cosmetic_speed_lifetime(int(e["ptype"]), float(e["vx"]), float(e["vy"]),
-                                              self.time_scale, num_steps, self.physics_dt)
-            vx.append(a); vy.append(b); life.append(c)
+        vx, vy, life = cosmetic_speed_lifetime_array(new["ptype"], new["vx"], new["vy"], self.time_scale,
+                                                     num_steps, self.physics_dt)
         born = dict(x=new["x"].astype(np.float64), y=new["y"].astype(np.float64),
-                    vx=np.array(vx), vy=np.array(vy), age=np.zeros(len(new)),
-                    lifetime=np.array(life), type=new["ptype"].astype(np.int32),
+                    vx=vx, vy=vy, age=np.zeros(len(new)),
+                    lifetime=life, type=new["ptype"].astype(np.int32),
                     nucleus=new["nucleus"].astype(np.int64))
         remaining = np.clip(num_steps - 1 - (new["step"].astype(np.int64) - step0), 0, num_steps)
         born = self._animate(born, remaining, eff_dt, step_time, num_steps)

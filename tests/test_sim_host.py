@@ -111,3 +111,23 @@ def test_time_scale_presets_match_reference():
     assert sim.TIME_SCALE_PRESETS["billion"] == 31557600000000000.0
     assert sim.TIME_SCALE_PRESETS["real"] == 1.0
     assert len(sim.TIME_SCALE_PRESETS) == 8
+
+
+def test_vectorised_cosmetics_equal_the_scalar_function_bit_for_bit(golden):
+    rng = np.random.default_rng(3)
+    n = 4000
+    ptype = rng.integers(0, 6, n)
+    ang = rng.random(n) * 2 * np.pi
+    speed = np.where(rng.random(n) < 0.02, 0.0, rng.random(n) * 300)
+    vx, vy = speed * np.cos(ang), speed * np.sin(ang)
+    for ts, sub, pdt in ((0.5, 3, 1 / 240), (1.0, 4, 1 / 240), (60.0, 16, 1 / 60), (3.15576e16, 20, 1 / 1000)):
+        ax, ay, al = sim.cosmetic_speed_lifetime_array(ptype, vx, vy, ts, sub, pdt)
+        for k in range(n):
+            bx, by, bl = sim.cosmetic_speed_lifetime(int(ptype[k]), float(vx[k]), float(vy[k]), ts, sub, pdt)
+            assert ax[k] == bx and ay[k] == by and al[k] == bl, (k, ts)
+    rows = golden["cosmetics"]
+    gx, gy, gl = sim.cosmetic_speed_lifetime_array(
+        np.array([r["ptype"] for r in rows[:20]]), np.array([fh(r["vx"]) for r in rows[:20]]),
+        np.array([fh(r["vy"]) for r in rows[:20]]), fh(rows[0]["time_scale"]), rows[0]["substeps"],
+        fh(rows[0]["physics_dt"]))
+    assert gl[0] == fh(rows[0]["lifetime"])
