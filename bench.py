@@ -282,6 +282,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()                   # no CPU fallback: fail loudly before anything else
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
