@@ -1,0 +1,39 @@
+"""Multi-GPU parity of the cloud schemes (skipped on boxes with fewer than 2 GPUs): launches
+scripts/check_cloud_multi.py under torchrun -- symmetric scheme with the fused peer-memory exchange and
+with the NCCL exchange must be BIT-IDENTICAL to the single-GPU run, replicas identical on all ranks."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cloud_schemes_bit_identical_across_gpus(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, found {torch.cuda.device_count()}")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "scripts", "check_cloud_multi.py"), "60001"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == world
+    for k in ("symmetric_peer", "symmetric_nccl", "ordered"):
+        assert out[k]["replicas_identical"], k
+    assert out["symmetric_peer"]["bit_identical"] and out["symmetric_nccl"]["bit_identical"]
