@@ -612,6 +612,7 @@ class DecayPopulation:
         self.table = device_table(self.dt_decay, dev)
         self.watch = [nuclides.zn_pack(z, n) for z, n in watch][:8]
         self.step_index = 0
+        self._desc = None
 
     def step(self, n_steps=1, uniforms=None, want_decisions=False):
         """Returns (counts[n_steps, 16] int64 tensor, decisions[n_steps, n] uint8 or None);
@@ -619,10 +620,12 @@ class DecayPopulation:
         dev = self.device
         counts = torch.zeros(n_steps, _lib.COUNT_COLS, dtype=torch.int64, device=dev)
         decided = torch.zeros(n_steps, self.n, dtype=torch.uint8, device=dev) if want_decisions else None
+        if self._desc is None:
+            self._desc = _lib.PopulationDesc()
         if uniforms is not None:
             uniforms = torch.as_tensor(uniforms, dtype=torch.float64).contiguous().to(dev)
             assert tuple(uniforms.shape) == (n_steps, self.n, 4)
-        d = _lib.PopulationDesc()
+        d = self._desc
         d.zn, d.half_life, d.p_decay = self.zn.data_ptr(), self.half_life.data_ptr(), self.p_decay.data_ptr()
         d.n, d.id_base, d.table, d.dt_decay = self.n, self.id_base, self.table.data_ptr(), self.dt_decay
         d.uniforms, d.uniforms_n = _lib.ptr(uniforms), self.n
