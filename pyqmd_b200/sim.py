@@ -225,6 +225,28 @@ class HeadlessSimulation:
         born = self._animate(born, remaining, eff_dt, step_time, num_steps)
         self.free = {k: np.concatenate([self.free[k], born[k]]) for k in self.free}
 
+    def free_particle_objects(self, k=None):
+        """The emitted particles still alive as ``Particle`` objects (what the app keeps in
+        ``self.particles``, nuclear_sim.py:349); ``k``: only those emitted by nucleus ``k``."""
+        from .types import Particle
+        f = self.free
+        sel = np.arange(len(f["x"])) if k is None else np.nonzero(f["nucleus"] == k)[0]
+        out = []
+        for i in sel:
+            p = Particle(float(f["x"][i]), float(f["y"][i]), ParticleType(int(f["type"][i])),
+                         float(f["vx"][i]), float(f["vy"][i]))
+            p.age, p.lifetime = float(f["age"][i]), float(f["lifetime"][i])
+            out.append(p)
+        return out
+
+    def render_args(self, k=0, camera_pos=(400.0, 400.0), zoom=15.0):
+        """Positional arguments of the reference's ``Renderer.render`` (rendering.py:32-34, called at
+        nuclear_sim.py:598-603) for nucleus ``k``: pygame can draw the GPU-resident state with
+        ``renderer.render(*sim.render_args(k))``."""
+        return (self.nucleus_view(k), self.free_particle_objects(k), list(camera_pos), zoom,
+                self.time_scale, self.accuracy, self.physics_dt, self.substeps_used, self.max_substeps,
+                True, dict(self.decay_counts), self.time_passed)
+
     def nucleus_view(self, k=0):
         """A ``Nucleus`` (pyqmd_b200.types) materialised from the device state of nucleus ``k`` --
         the render bridge: ``Renderer`` reads ``.particles[i].x/.y/.type/.radius`` and

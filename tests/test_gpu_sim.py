@@ -85,3 +85,29 @@ def test_alpha_chain_with_projection_keeps_nuclei_physical():
     assert abs(xs.mean() - 400.0) < 30 and abs(ys.mean() - 400.0) < 30      # origin (400, 400), :93
     ext = np.hypot(xs - xs.mean(), ys - ys.mean()).max()
     assert 10.0 < ext < 200.0
+
+
+def test_render_bridge_feeds_the_reference_renderer_signature():
+    """render_args(k) = the twelve positional arguments of Renderer.render (rendering.py:32-34); the
+    objects carry every attribute the renderer reads (rendering.py:42-48, 135-246)."""
+    sim = HeadlessSimulation((6, 8), n_nuclei=64, seed=2)
+    T = nuclides.get_half_life(6, 8)
+    sim.time_scale = T / 5 * 60                      # a fifth of a half-life per frame
+    for _ in range(4):
+        sim.update_simulation(1 / 60)
+    assert sum(sim.decay_counts.values()) > 0
+    k = int(np.nonzero(sim.ensemble.zn.cpu().numpy() == nuclides.zn_pack(7, 7))[0][0])   # a decayed one
+    args = sim.render_args(k)
+    assert len(args) == 12
+    nucleus, particles, camera_pos, zoom, time_scale, accuracy, physics_dt, substeps, max_substeps, \
+        gpu_available, decay_counts, time_passed = args
+    assert (nucleus.protons, nucleus.neutrons) == (7, 7) and len(nucleus.particles) == 14
+    for p in sorted(nucleus.particles, key=lambda q: q.y):          # what render() does first
+        assert p.radius == 2.5 and p.type in (ParticleType.PROTON, ParticleType.NEUTRON)
+        assert len(p.get_color()) == 3 and abs(p.x - 400) < 200
+    assert len(particles) == 1 and particles[0].type == ParticleType.ELECTRON
+    fade = particles[0].age / particles[0].lifetime                 # rendering.py:47
+    assert 0.0 <= fade < 1.0
+    assert gpu_available is True and substeps == sim.substeps_used and max_substeps == 20
+    assert set(decay_counts) == {d.name for d in DecayType if d != DecayType.NONE}
+    assert time_passed == sim.time_passed and time_scale == sim.time_scale
