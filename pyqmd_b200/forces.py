@@ -84,6 +84,21 @@ class NuclearForces:
         if particles and n_steps > 0:
             self._update_f64(particles, dt, n_steps)
 
+    def step_arrays(self, x, y, vx, vy, is_proton, dt, n_steps=1):
+        """The same update on caller-owned float64 numpy arrays (updated in place), for callers that
+        keep their state in arrays rather than in ``Particle`` objects: no per-object marshalling."""
+        n = len(x)
+        if n == 0 or n_steps <= 0:
+            return
+        for a in (x, y, vx, vy):
+            if a.dtype != np.float64 or not a.flags.c_contiguous or len(a) != n:
+                raise ValueError("x, y, vx, vy must be C-contiguous float64 arrays of equal length")
+        isp = np.ascontiguousarray(is_proton, dtype=np.uint8)
+        rc = _lib.lib().pyqmd_update_particles_f64(
+            x.ctypes.data, y.ctypes.data, vx.ctypes.data, vy.ctypes.data, isp.ctypes.data, n,
+            self.strong_strength, self.coulomb_strength, self.pauli_strength, dt, n_steps)
+        _lib.check(rc, "pyqmd_update_particles_f64")
+
     def _update_f64(self, particles, dt, n_steps=1):
         n = len(particles)
         x = np.fromiter((p.x for p in particles), np.float64, n)

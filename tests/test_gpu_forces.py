@@ -265,3 +265,22 @@ def test_branch_census_matches_oracle_statistics():
     for name in tot:
         assert abs(tot[name] - counts[name]) <= 4 + 1e-4 * tot[name], (name, tot[name], counts[name])
     assert abs(flops / pairs - flops_pair) < 1e-3
+
+
+def test_step_arrays_equals_particle_list_path():
+    """NuclearForces.step_arrays (numpy state, in place) == the list-of-Particle path, bit for bit."""
+    from pyqmd_b200.forces import NuclearForces
+    from pyqmd_b200.types import Particle, ParticleType
+    rng = np.random.default_rng(8)
+    n = 238
+    x, y = rng.uniform(390, 410, n), rng.uniform(390, 410, n)
+    vx, vy = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    isp = (rng.random(n) < 0.4).astype(np.uint8)
+    ps = [Particle(float(a), float(b), ParticleType.PROTON if t else ParticleType.NEUTRON, float(c), float(d))
+          for a, b, c, d, t in zip(x, y, vx, vy, isp)]
+    nf = NuclearForces()
+    nf.step(ps, 1 / 240, 3)
+    nf.step_arrays(x, y, vx, vy, isp, 1 / 240, 3)
+    assert np.array_equal(x, [p.x for p in ps]) and np.array_equal(vy, [p.vy for p in ps])
+    with pytest.raises(ValueError):
+        nf.step_arrays(x.astype(np.float32), y, vx, vy, isp, 1 / 240)
