@@ -234,6 +234,32 @@ typedef struct {
 int pyqmd_ensemble_step(const pyqmd_ensemble *e, int32_t n_steps, void *stream);
 
 /*
+ * The same sub-steps for an ensemble whose state lives in HOST memory -- the shape of the reference's
+ * per-step call (nuclear_forces.py:190-234: pack, upload, kernel, download, write back) for many
+ * nuclei: every call uploads pos / vel / is_proton, runs n_steps sub-steps and downloads pos / vel
+ * (and is_proton / count / zn when decay is enabled).  The work is cut into `n_chunks` chunks that
+ * flow through three in-order lanes (upload, compute, download) linked by events, so both copy
+ * engines run back to back and the kernels hide under them.  Host arrays should be pinned.
+ *   e          descriptor whose pointers are DEVICE buffers of the same layout (staging area)
+ *   h_*        host arrays with the layout of e->pos, e->vel, e->is_proton, e->count, e->zn
+ *   chunks     n_chunks descriptors: nuclei [nuc0, nuc1), slots [slot0, slot1) and the kernel
+ *              launches of the chunk (one per size bin: cap, DEVICE index list, its length)
+ * Stream-ordered on `stream`, non-blocking.
+ */
+#define PYQMD_MAX_CHUNK_LAUNCHES 12
+typedef struct {
+    int64_t nuc0, nuc1, slot0, slot1;
+    int32_t n_launch;
+    int32_t cap[PYQMD_MAX_CHUNK_LAUNCHES];
+    const int32_t *list[PYQMD_MAX_CHUNK_LAUNCHES];
+    int64_t n_list[PYQMD_MAX_CHUNK_LAUNCHES];
+} pyqmd_host_chunk;
+
+int pyqmd_ensemble_step_host(const pyqmd_ensemble *e, float *h_pos, float *h_vel, uint8_t *h_is_proton,
+                             int32_t *h_count, int32_t *h_zn, const pyqmd_host_chunk *chunks,
+                             int32_t n_chunks, int32_t n_steps, void *stream);
+
+/*
  * Per-frame overlap projection of every listed nucleus: NuclearSimulation.resolve_overlaps,
  * nuclear_sim.py:355-379 (sequential i < j sweep, minimum distance 5.0, immediate updates), run
  * once per frame after the sub-steps (:175-176).  Only pos / offset / count / list / cap /

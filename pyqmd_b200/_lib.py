@@ -26,7 +26,7 @@ EXPORTS = (
     "pyqmd_cloud_workspace_bytes", "pyqmd_cloud_step", "pyqmd_cloud_sort_keys",
     "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_integrate",
     "pyqmd_cloud_exchange_integrate",
-    "pyqmd_ensemble_step", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
+    "pyqmd_ensemble_step", "pyqmd_ensemble_step_host", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
     "pyqmd_ensemble_init_layout",
     "pyqmd_population_step",
 )
@@ -62,6 +62,18 @@ class EnsembleDesc(C.Structure):
         ("seed", C.c_uint64), ("step0", C.c_uint32), ("reserved", C.c_uint32),
         ("events", C.c_void_p), ("event_capacity", C.c_int64), ("event_count", C.c_void_p),
         ("mode_counts", C.c_void_p),
+    ]
+
+
+MAX_CHUNK_LAUNCHES = 12
+
+
+class HostChunk(C.Structure):
+    """pyqmd_host_chunk"""
+    _fields_ = [
+        ("nuc0", C.c_int64), ("nuc1", C.c_int64), ("slot0", C.c_int64), ("slot1", C.c_int64),
+        ("n_launch", C.c_int32), ("cap", C.c_int32 * MAX_CHUNK_LAUNCHES),
+        ("list", C.c_void_p * MAX_CHUNK_LAUNCHES), ("n_list", C.c_int64 * MAX_CHUNK_LAUNCHES),
     ]
 
 
@@ -106,6 +118,8 @@ def lib():
     L.pyqmd_cloud_integrate.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, vp, vp, vp]
     L.pyqmd_cloud_exchange_integrate.argtypes = [vp, vp, vp, i64, i64, i64, f32, vp, vp, i32, vp, vp]
     L.pyqmd_ensemble_step.argtypes = [C.POINTER(EnsembleDesc), i32, vp]
+    L.pyqmd_ensemble_step_host.argtypes = [C.POINTER(EnsembleDesc), vp, vp, vp, vp, vp,
+                                           C.POINTER(HostChunk), i32, i32, vp]
     L.pyqmd_resolve_overlaps.argtypes = [C.POINTER(EnsembleDesc), vp, i32, vp, vp]
     L.pyqmd_ensemble_census.argtypes = [C.POINTER(EnsembleDesc), vp, vp]
     L.pyqmd_ensemble_init_layout.argtypes = [C.POINTER(EnsembleDesc), C.POINTER(C.c_double), vp,

@@ -161,9 +161,100 @@ static int prepare_scratch(HostPathScratch& S, int64_t n)
     return S.ensure(3 * b_pos + b_isp + 256 + ws + 256, 2 * b_pos + b_isp);
 }
 
+// ---- host-buffer ensemble pipeline: three in-order lanes linked by per-chunk events ------------------
+struct HostPipeline {
+    std::mutex mu;
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_up, ev_run;
+
+    int ensure(int n_chunks)
+    {
+        if (!up) {
+            PYQMD_CUDA_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+            PYQMD_CUDA_CHECK(cudaStreamCreateWithFlags(&run, cudaStreamNonBlocking));
+            PYQMD_CUDA_CHECK(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+            PYQMD_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            for (auto& j : join) PYQMD_CUDA_CHECK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
+        }
+        while ((int)ev_up.size() < n_chunks) {
+            cudaEvent_t a, b;
+            PYQMD_CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            PYQMD_CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            ev_up.push_back(a);
+            ev_run.push_back(b);
+        }
+        return PYQMD_OK;
+    }
+};
+static HostPipeline g_pipe;
+
 }  // namespace pyqmd
 
 using namespace pyqmd;
+
+extern "C" int pyqmd_ensemble_step_host(const pyqmd_ensemble* e, float* h_pos, float* h_vel,
+                                        uint8_t* h_is_proton, int32_t* h_count, int32_t* h_zn,
+                                        const pyqmd_host_chunk* chunks, int32_t n_chunks,
+                                        int32_t n_steps, void* stream)
+{
+    PYQMD_REQUIRE(e != nullptr && chunks != nullptr && n_chunks >= 0 && n_steps >= 0, "arguments");
+    PYQMD_REQUIRE(h_pos && h_vel && h_is_proton, "host arrays");
+    PYQMD_REQUIRE(e->pos && e->vel && e->is_proton && e->offset && e->count, "device staging arrays");
+    if (e->decay_enabled) PYQMD_REQUIRE(h_count && h_zn && e->zn, "count / zn arrays (decay enabled)");
+    if (n_chunks == 0 || n_steps == 0) return PYQMD_OK;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    int rc = g_pipe.ensure(n_chunks);
+    if (rc != PYQMD_OK) return rc;
+    cudaStream_t user = (cudaStream_t)stream;
+    PYQMD_CUDA_CHECK(cudaEventRecord(g_pipe.fork, user));
+    PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.up, g_pipe.fork, 0));
+    PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.run, g_pipe.fork, 0));
+    PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.down, g_pipe.fork, 0));
+    for (int k = 0; k < n_chunks; ++k) {
+        const pyqmd_host_chunk& c = chunks[k];
+        PYQMD_REQUIRE(c.slot0 >= 0 && c.slot0 <= c.slot1 && c.nuc0 >= 0 && c.nuc0 <= c.nuc1 &&
+                      c.nuc1 <= e->n_nuclei && c.n_launch >= 0 && c.n_launch <= PYQMD_MAX_CHUNK_LAUNCHES,
+                      "chunk descriptor");
+        const size_t ns = (size_t)(c.slot1 - c.slot0), nn = (size_t)(c.nuc1 - c.nuc0);
+        PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->pos + 2 * c.slot0, h_pos + 2 * c.slot0, 8 * ns,
+                                         cudaMemcpyHostToDevice, g_pipe.up));
+        PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->vel + 2 * c.slot0, h_vel + 2 * c.slot0, 8 * ns,
+                                         cudaMemcpyHostToDevice, g_pipe.up));
+        PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->is_proton + c.slot0, h_is_proton + c.slot0, ns,
+                                         cudaMemcpyHostToDevice, g_pipe.up));
+        PYQMD_CUDA_CHECK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
+        PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
+        for (int l = 0; l < c.n_launch; ++l) {
+            pyqmd_ensemble d = *e;
+            d.cap = c.cap[l];
+            d.list = c.list[l];
+            d.n_list = c.n_list[l];
+            rc = pyqmd_ensemble_step(&d, n_steps, g_pipe.run);
+            if (rc != PYQMD_OK) return rc;
+        }
+        PYQMD_CUDA_CHECK(cudaEventRecord(g_pipe.ev_run[k], g_pipe.run));
+        PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.down, g_pipe.ev_run[k], 0));
+        PYQMD_CUDA_CHECK(cudaMemcpyAsync(h_pos + 2 * c.slot0, e->pos + 2 * c.slot0, 8 * ns,
+                                         cudaMemcpyDeviceToHost, g_pipe.down));
+        PYQMD_CUDA_CHECK(cudaMemcpyAsync(h_vel + 2 * c.slot0, e->vel + 2 * c.slot0, 8 * ns,
+                                         cudaMemcpyDeviceToHost, g_pipe.down));
+        if (e->decay_enabled) {
+            PYQMD_CUDA_CHECK(cudaMemcpyAsync(h_is_proton + c.slot0, e->is_proton + c.slot0, ns,
+                                             cudaMemcpyDeviceToHost, g_pipe.down));
+            PYQMD_CUDA_CHECK(cudaMemcpyAsync(h_count + c.nuc0, e->count + c.nuc0, 4 * nn,
+                                             cudaMemcpyDeviceToHost, g_pipe.down));
+            PYQMD_CUDA_CHECK(cudaMemcpyAsync(h_zn + c.nuc0, e->zn + c.nuc0, 4 * nn,
+                                             cudaMemcpyDeviceToHost, g_pipe.down));
+        }
+    }
+    cudaStream_t lanes[3] = {g_pipe.up, g_pipe.run, g_pipe.down};
+    for (int l = 0; l < 3; ++l) {
+        PYQMD_CUDA_CHECK(cudaEventRecord(g_pipe.join[l], lanes[l]));
+        PYQMD_CUDA_CHECK(cudaStreamWaitEvent(user, g_pipe.join[l], 0));
+    }
+    return PYQMD_OK;
+}
 
 extern "C" int pyqmd_abi_version(void) { return PYQMD_ABI_VERSION; }
 

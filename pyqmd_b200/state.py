@@ -350,11 +350,11 @@ class NucleusEnsemble:
 class HostEnsembleRunner:
     """End-to-end path with HOST-resident state, the shape of the reference's per-step call
     (nuclear_forces.py:190-234: pack -> H2D -> kernel -> D2H -> write back): the ensemble lives in
-    pinned host memory; every ``step`` uploads it, runs the sub-steps and downloads it again.
-    The nuclei are cut into chunks that flow through a few CUDA streams, so the upload of chunk
-    k+1, the kernel of chunk k and the download of chunk k-1 overlap."""
+    pinned host memory; every ``step`` uploads it, runs the sub-steps and downloads it again -- one
+    C-ABI call, pyqmd_ensemble_step_host, which cuts the nuclei into chunks and streams them through
+    three in-order lanes (upload, compute, download), so both PCIe directions and the kernels overlap."""
 
-    def __init__(self, ens: NucleusEnsemble, chunks=8, n_streams=4):
+    def __init__(self, ens: NucleusEnsemble, chunks=8):
         self.ens = ens
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         self.h_pos, self.h_vel, self.h_isp = pin(ens.pos), pin(ens.vel), pin(ens.is_proton)
@@ -365,24 +365,28 @@ class HostEnsembleRunner:
         chunks = max(1, min(chunks, n))
         bounds = [round(k * n / chunks) for k in range(chunks + 1)]
         dev = ens.device
-        self.lists = []
+        assert len(ens.bins) <= _lib.MAX_CHUNK_LAUNCHES
+        self.lists = []          # per size bin: (cap, device index list, host copy)
         for cap, lst, n_list in ens.bins:
             idx = (np.arange(n, dtype=np.int32) if lst is None else lst.cpu().numpy())
             self.lists.append((cap, torch.from_numpy(idx).to(dev), idx))
-        self.chunks = []
+        rows = []
         for a, b in zip(bounds[:-1], bounds[1:]):
             if b <= a:
                 continue
-            s0 = int(off[a])
-            s1 = int(off[b - 1] + cnt[b - 1])
-            launches = []
+            c = _lib.HostChunk()
+            c.nuc0, c.nuc1 = a, b
+            c.slot0, c.slot1 = int(off[a]), int(off[b - 1] + cnt[b - 1])
+            k = 0
             for cap, lst_dev, idx in self.lists:
                 lo, hi = np.searchsorted(idx, a), np.searchsorted(idx, b)
                 if hi > lo:
-                    launches.append((cap, lst_dev.data_ptr() + 4 * int(lo), int(hi - lo)))
-            self.chunks.append((a, b, s0, s1, launches))
-        self.n_chunks = len(self.chunks)
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, self.n_chunks))]
+                    c.cap[k], c.list[k], c.n_list[k] = cap, lst_dev.data_ptr() + 4 * int(lo), int(hi - lo)
+                    k += 1
+            c.n_launch = k
+            rows.append(c)
+        self.n_chunks = len(rows)
+        self.chunk_array = (_lib.HostChunk * self.n_chunks)(*rows)
         self.h2d_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes + self.h_isp.nbytes)
         # without decay the types / counts / (Z, N) cannot change: only positions and velocities
         # come back, like the reference's download (nuclear_forces.py:227)
@@ -391,25 +395,11 @@ class HostEnsembleRunner:
 
     def step(self, n_steps=1):
         ens = self.ens
-        cur = torch.cuda.current_stream()
-        for s in self.streams:
-            s.wait_stream(cur)
-        for k, (a, b, s0, s1, launches) in enumerate(self.chunks):
-            st = self.streams[k % len(self.streams)]
-            with torch.cuda.stream(st):
-                ens.pos[s0:s1].copy_(self.h_pos[s0:s1], non_blocking=True)
-                ens.vel[s0:s1].copy_(self.h_vel[s0:s1], non_blocking=True)
-                ens.is_proton[s0:s1].copy_(self.h_isp[s0:s1], non_blocking=True)
-                for cap, lst_ptr, n_list in launches:
-                    ens.launch(cap, lst_ptr, n_list, n_steps, st.cuda_stream)
-                self.h_pos[s0:s1].copy_(ens.pos[s0:s1], non_blocking=True)
-                self.h_vel[s0:s1].copy_(ens.vel[s0:s1], non_blocking=True)
-                if ens.decay:
-                    self.h_isp[s0:s1].copy_(ens.is_proton[s0:s1], non_blocking=True)
-                    self.h_count[a:b].copy_(ens.count[a:b], non_blocking=True)
-                    self.h_zn[a:b].copy_(ens.zn[a:b], non_blocking=True)
-        for s in self.streams:
-            cur.wait_stream(s)
+        d = ens._desc(1, None, 0, None)
+        _lib.check(_lib.lib().pyqmd_ensemble_step_host(
+            C.byref(d), self.h_pos.data_ptr(), self.h_vel.data_ptr(), self.h_isp.data_ptr(),
+            self.h_count.data_ptr(), self.h_zn.data_ptr(), self.chunk_array, self.n_chunks, n_steps,
+            _lib.current_stream()), "pyqmd_ensemble_step_host")
         ens.step_index += n_steps
 
 

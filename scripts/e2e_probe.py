@@ -12,7 +12,7 @@ out={}
 h=torch.empty(232*1024*1024, dtype=torch.uint8, pin_memory=True); d=torch.empty_like(h, device='cuda')
 out['h2d_GBs']=h.numel()/t(lambda: d.copy_(h, non_blocking=True),5)/1e6
 out['d2h_GBs']=h.numel()/t(lambda: h.copy_(d, non_blocking=True),5)/1e6
-for chunks, streams in ((1,1),(4,4),(8,4),(16,4),(16,8),(32,8),(64,8)):
-    r=HostEnsembleRunner(ens, chunks=chunks, n_streams=streams)
+for chunks, streams in ((4,3),(8,3),(16,3),(24,3),(32,3),(64,3)):
+    r=HostEnsembleRunner(ens, chunks=chunks)
     out[f'e2e_ms_c{chunks}_s{streams}']=t(lambda: r.step(1),8)
 print(json.dumps(out))
