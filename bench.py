@@ -336,70 +336,6 @@ def main():
     line["clocks"] = clocks
     line["gpu_launches"] = launches
 
-    if not args.no_extras and args.workload == "ensemble":
-        # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection, from a
-        # settled state (fresh layouts + 12 frames; the step-only state above has collapsed)
-        from pyqmd_b200.state import NucleusEnsemble
-        n_f = ens.n_nuclei
-        del ens
-        torch.cuda.empty_cache()
-        ens = NucleusEnsemble.from_templates((PB208,), n_f, device=dev, id_base=rank * n_f, decay=False)
-        for _ in range(12):
-            ens.frame(4)
-        p0 = int(ens.push_count.item())
-        sec_f = timed_steps(lambda: ens.frame(4), 10, 1, dist, torch)
-        pushes = (int(ens.push_count.item()) - p0) / 11 / n_f
-        sec_s = timed_steps(lambda: ens.step(4), 10, 1, dist, torch)
-        census_f, flops_f = ens.census(range(0, n_f, max(1, n_f // 256)))
-        frame = {"ms_per_frame": sec_f / 10 * 1e3, "substeps_per_frame": 4,
-                 "ms_4_substeps_alone": sec_s / 10 * 1e3,
-                 "nucleus_frames_per_s": float(tot_nuc.item()) * 10 / sec_f,
-                 "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 10 / sec_f,
-                 "pushes_per_nucleus_frame": pushes, "flops_per_pair": flops_f,
-                 "branch_census": census_f,
-                 "note": "4 sub-steps + resolve_overlaps per frame, device resident, settled nuclei"}
-        del ens
-        torch.cuda.empty_cache()
-        keep = ("metric", "unit", "value", "ms_per_step", "config", "roofline", "scaling",
-                "nucleus_steps_per_s", "decays")
-        also = {"frame": frame}
-        extra = bench_cloud(args, 2, 1, rank, world, dev, dist, torch, None, fp32_peak,
-                            (f1.value, f2.value, nominal))
-        also["cloud"] = {k: extra[k] for k in keep if k in extra}
-        torch.cuda.empty_cache()
-        extra, ens3, _, _ = bench_ensemble(args, "mixed", 5, 3, rank, world, dev, dist, torch, None,
-                                           fp32_peak, (f1.value, f2.value, nominal), hbm_peak, hbm_src,
-                                           with_e2e=False)
-        also["mixed"] = {k: extra[k] for k in keep if k in extra}
-        del ens3
-        torch.cuda.empty_cache()
-        extra = bench_decay(args, 3, 3, rank, world, dev, dist, torch, None, hbm_peak, hbm_src)
-        also["decay"] = {k: extra[k] for k in keep if k in extra}
-        torch.cuda.empty_cache()
-        if rank == 0:
-            also["c1"] = bench_c1(dev, torch)
-        if rank == 0 and world == 1:
-            # the reference's CPU path (C port, all host threads) beside each config
-            from oracle import oracle as orc
-            threads = orc.max_threads()
-            v, dt_s = cpu_cloud_sample(65536, 1024 * threads, threads)
-            also["cloud"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                             "sample": f"{1024 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
-            v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 10, threads)
-            also["mixed"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "nucleus_steps_per_s": ns,
-                                             "cores": threads, "kind": "port",
-                                             "sample": f"{9 * 32 * threads} nuclei x 10 sub-steps, {dt_s:.1f} s"}
-            n_d = 4_000_000 * threads
-            Tn = np.full(n_d, 180825048000.0)
-            un = np.random.default_rng(1).random(n_d)
-            t0 = time.perf_counter()
-            orc.decay_decisions(Tn, 180825048000.0 * 1e-3, un, n_threads=threads)
-            dt_s = time.perf_counter() - t0
-            also["decay"]["cpu_baseline"] = {"value": n_d / dt_s, "unit": "nucleus-steps/s", "cores": threads,
-                                             "kind": "port",
-                                             "sample": f"{n_d} should_decay decisions with supplied uniforms, {dt_s:.2f} s"}
-        line["also"] = also
-
     if rank == 0 and world == 1:
         from oracle import oracle as orc
         threads = orc.max_threads()
@@ -416,6 +352,77 @@ def main():
                                     "nucleus_steps_per_s": ns,
                                     "sample": f"{n_s} nuclei x 30 sub-steps of the same workload, "
                                               f"{dt:.1f} s, OpenMP over nuclei"}
+
+    if not args.no_extras and args.workload == "ensemble":
+        # every other config of BASELINE.json in the same line; a failure here must not cost the headline
+        try:
+            # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection, from a
+            # settled state (fresh layouts + 12 frames; the step-only state above has collapsed)
+            from pyqmd_b200.state import NucleusEnsemble
+            n_f = ens.n_nuclei
+            del ens
+            torch.cuda.empty_cache()
+            ens = NucleusEnsemble.from_templates((PB208,), n_f, device=dev, id_base=rank * n_f, decay=False)
+            for _ in range(12):
+                ens.frame(4)
+            p0 = int(ens.push_count.item())
+            sec_f = timed_steps(lambda: ens.frame(4), 10, 1, dist, torch)
+            pushes = (int(ens.push_count.item()) - p0) / 11 / n_f
+            sec_s = timed_steps(lambda: ens.step(4), 10, 1, dist, torch)
+            census_f, flops_f = ens.census(range(0, n_f, max(1, n_f // 256)))
+            frame = {"ms_per_frame": sec_f / 10 * 1e3, "substeps_per_frame": 4,
+                     "ms_4_substeps_alone": sec_s / 10 * 1e3,
+                     "nucleus_frames_per_s": float(tot_nuc.item()) * 10 / sec_f,
+                     "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 10 / sec_f,
+                     "pushes_per_nucleus_frame": pushes, "flops_per_pair": flops_f,
+                     "branch_census": census_f,
+                     "note": "4 sub-steps + resolve_overlaps per frame, device resident, settled nuclei"}
+            del ens
+            torch.cuda.empty_cache()
+            keep = ("metric", "unit", "value", "ms_per_step", "config", "roofline", "scaling",
+                    "nucleus_steps_per_s", "decays")
+            also = {"frame": frame}
+            extra = bench_cloud(args, 2, 1, rank, world, dev, dist, torch, None, fp32_peak,
+                                (f1.value, f2.value, nominal))
+            also["cloud"] = {k: extra[k] for k in keep if k in extra}
+            torch.cuda.empty_cache()
+            extra, ens3, _, _ = bench_ensemble(args, "mixed", 5, 3, rank, world, dev, dist, torch, None,
+                                               fp32_peak, (f1.value, f2.value, nominal), hbm_peak, hbm_src,
+                                               with_e2e=False)
+            also["mixed"] = {k: extra[k] for k in keep if k in extra}
+            del ens3
+            torch.cuda.empty_cache()
+            extra = bench_decay(args, 3, 3, rank, world, dev, dist, torch, None, hbm_peak, hbm_src)
+            also["decay"] = {k: extra[k] for k in keep if k in extra}
+            torch.cuda.empty_cache()
+            if rank == 0:
+                also["c1"] = bench_c1(dev, torch)
+            if rank == 0 and world == 1:
+                # the reference's CPU path (C port, all host threads) beside each config
+                from oracle import oracle as orc
+                threads = orc.max_threads()
+                v, dt_s = cpu_cloud_sample(65536, 1024 * threads, threads)
+                also["cloud"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                                 "sample": f"{1024 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
+                v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 10, threads)
+                also["mixed"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "nucleus_steps_per_s": ns,
+                                                 "cores": threads, "kind": "port",
+                                                 "sample": f"{9 * 32 * threads} nuclei x 10 sub-steps, {dt_s:.1f} s"}
+                n_d = 4_000_000 * threads
+                Tn = np.full(n_d, 180825048000.0)
+                un = np.random.default_rng(1).random(n_d)
+                t0 = time.perf_counter()
+                orc.decay_decisions(Tn, 180825048000.0 * 1e-3, un, n_threads=threads)
+                dt_s = time.perf_counter() - t0
+                also["decay"]["cpu_baseline"] = {"value": n_d / dt_s, "unit": "nucleus-steps/s", "cores": threads,
+                                                 "kind": "port",
+                                                 "sample": f"{n_d} should_decay decisions with supplied uniforms, {dt_s:.2f} s"}
+            line["also"] = also
+        except Exception as exc:      # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            line.setdefault("also", {})["error"] = repr(exc)[:300]
+
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
