@@ -318,3 +318,22 @@ def test_host_buffer_pipeline_equals_device_resident_steps(decay):
             assert torch.equal(run.h_zn, ref.zn.cpu()) and torch.equal(run.h_count, ref.count.cpu())
             assert torch.equal(run.h_isp[live], ref.is_proton.cpu()[live])
             assert int(ens.mode_counts.sum()) == int(ref.mode_counts.sum()) > 0
+
+
+@pytest.mark.parametrize("n", [300, 513, 700, 1024, 1025, 1500])
+def test_single_system_sizes_through_the_host_api(n):
+    """One system of n nucleons through NuclearForces.step_arrays: <= 512 the pair kernel, 513..1024
+    the one-nucleon-per-thread kernel, > 1024 the tiled cloud path -- all against the oracle."""
+    from pyqmd_b200.forces import NuclearForces
+    rng = np.random.default_rng(n)
+    R = 2.5 * np.sqrt(n)
+    r, th = R * np.sqrt(rng.random(n)), 2 * np.pi * rng.random(n)
+    x32, y32 = (r * np.cos(th)).astype(np.float32), (r * np.sin(th)).astype(np.float32)
+    isp = (rng.random(n) < 0.4).astype(np.uint8)
+    x, y = x32.astype(np.float64), y32.astype(np.float64)
+    vx, vy = np.zeros(n), np.zeros(n)
+    p0 = np.stack([x32, y32], 1)
+    ox, oy, _, _, _, _, amb = oracle_step(p0, np.zeros_like(p0), isp, 1 / 240)
+    NuclearForces().step_arrays(x, y, vx, vy, isp, 1 / 240)
+    got = np.stack([x, y], 1).astype(np.float32)
+    assert pos_error(p0, got, ox, oy, amb) <= POS_TOL
