@@ -267,3 +267,27 @@ def test_full_size_cloud_1M_properties():
     got = cloud.pos[:n].cpu().numpy().astype(np.float64)
     want = p_sorted.astype(np.float64) + 0.85 * F * cloud.dt ** 2
     assert np.abs(got - want).max() / extent_of(p_sorted) <= POS_TOL
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_random_clouds_against_oracle(seed):
+    """Randomised differential test: random size, density, proton fraction, strengths, scheme and
+    ordering; forces of one step against the float64 oracle."""
+    from pyqmd_b200.state import NucleonCloud
+    rng = np.random.default_rng(seed)
+    for _ in range(6):
+        n = int(rng.integers(2, 7000))
+        density = float(rng.choice([1 / 4, 1 / 25, 1 / 100]))
+        frac_p = float(rng.choice([0.0, 0.1, 0.4, 0.9, 1.0]))
+        st = (float(rng.uniform(1, 300)), float(rng.uniform(0, 60)), float(rng.uniform(0, 60)))
+        scheme = str(rng.choice(SCHEMES))
+        sort = bool(rng.random() < 0.7)
+        pos, isp = make_cloud(n, seed=int(rng.integers(1 << 30)), frac_p=frac_p, density=density)
+        cloud = NucleonCloud(pos, isp, keep_force=True, strengths=st, scheme=scheme, sort=sort)
+        cloud.step(1)
+        F = cloud.forces().cpu().numpy().astype(np.float64)
+        fx, fy = oracle_forces(pos, isp, 0, n, strengths=st)
+        amb = ambiguous_mask(pos, 0, n)
+        Fo = np.stack([fx, fy], 1)
+        if np.abs(Fo[~amb]).max() > 0:
+            assert rel_l2(F, Fo, amb) <= FORCE_TOL, (n, density, frac_p, st, scheme, sort)
