@@ -312,3 +312,41 @@ def test_full_size_mixed_ensemble_1M_properties():
     n_c14 = len(range(3, n, 9))
     expect = n_c14 * (1 - (1 - p) ** 5)
     assert abs(events - expect) < 5 * np.sqrt(expect) + 1
+
+
+def test_random_nuclides_walk_the_same_chains_as_the_oracle():
+    """Randomised differential test over the whole (Z, N) plane -- tabulated chains and the
+    heuristic rules (beta+-, alpha, n / p emission, estimated half-lives): 20,000 random nuclides
+    followed for 12 sub-steps with supplied uniforms and a dt that makes most finite half-lives fire."""
+    from pyqmd_b200.state import DecayPopulation
+    rng = np.random.default_rng(2718)
+    n, steps = 20_000, 12
+    z = rng.integers(1, 100, n)
+    nn = np.clip((z * rng.uniform(0.7, 1.8, n)).astype(np.int64) + rng.integers(-2, 3, n), 0, 170)
+    dt = 1e9                                                   # ~ 30 years per sub-step
+    T0 = np.array([dor.half_life(int(a), int(b), 0.5)[0] for a, b in zip(z, nn)])
+    pop = DecayPopulation(((z << 16) | nn).astype(np.int32), dt_decay=dt, half_life=T0,
+                          p_decay=np.array([orc.decay_probability(t, dt) for t in T0]))
+    uni = rng.random((steps, n, 4))
+    counts, dec = pop.step(steps, uniforms=uni, want_decisions=True)
+    dec = dec.cpu().numpy().astype(bool)
+    cur_z, cur_n, T = z.copy(), nn.copy(), T0.copy()
+    modes = np.zeros(8, np.int64)
+    for s in range(steps):
+        want, _ = orc.decay_decisions(T, dt, uni[s, :, 0])
+        assert np.array_equal(dec[s], want), s
+        for k in np.nonzero(want)[0]:
+            nz, nk, mode, _ = dor.decay_product(int(cur_z[k]), int(cur_n[k]), uni[s, k, 1])
+            if mode is None:
+                continue
+            modes[int(mode)] += 1
+            cur_z[k], cur_n[k] = nz, nk
+            T[k] = dor.half_life(nz, nk, uni[s, k, 3])[0]
+    assert np.array_equal(pop.zn.cpu().numpy(), ((cur_z << 16) | cur_n).astype(np.int32))
+    gT = pop.half_life.cpu().numpy()
+    fin = np.isfinite(T)
+    assert np.array_equal(np.isfinite(gT), fin)
+    assert np.allclose(gT[fin], T[fin], rtol=4e-16, atol=0)
+    got_modes = counts[:, :8].sum(0).cpu().numpy()
+    assert np.array_equal(got_modes, modes)
+    assert (modes[[1, 2, 3]] > 100).all() and modes[5] + modes[6] > 0     # alpha, beta-, beta+, n / p emission
