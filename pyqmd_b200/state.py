@@ -57,6 +57,17 @@ def device_table(dt_decay: float, device) -> torch.Tensor:
     return _TABLE_CACHE[key]
 
 
+def check_table_range(zn: torch.Tensor):
+    """The dense device table covers Z < 128, N < 192 (PYQMD_TABLE_ZDIM / NDIM, every real nuclide);
+    the reference's heuristics accept any integers, so refuse what the table cannot follow."""
+    if zn.numel() == 0:
+        return
+    z, n = zn >> 16, zn & 0xFFFF
+    if int(z.max()) >= _lib.TABLE_ZDIM or int(n.max()) >= _lib.TABLE_NDIM or int(z.min()) < 0:
+        raise ValueError(f"(Z, N) outside the nuclide table: Z < {_lib.TABLE_ZDIM}, N < {_lib.TABLE_NDIM} "
+                         f"required, got Z up to {int(z.max())}, N up to {int(n.max())}")
+
+
 def initial_half_lives(zn: np.ndarray, dt_decay: float, rng: np.random.Generator):
     """Per-nucleus half-life and per-sub-step decay probability at creation
     (nuclear_sim.py:116 -> get_half_life; particles.py:134-144)."""
@@ -96,6 +107,8 @@ class NucleusEnsemble:
         as_t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray)
                                              else a, dtype=dt).contiguous().to(dev)
         self.zn = as_t(zn, torch.int32)
+        if decay:
+            check_table_range(self.zn)
         self.offsets = as_t(offsets, torch.int64)
         self.count = as_t(counts, torch.int32)
         self.pos = as_t(pos, torch.float32).reshape(-1, 2).contiguous()
@@ -583,6 +596,7 @@ class DecayPopulation:
         _lib.require_cuda()
         dev = self.device = torch.device(device)
         self.zn = torch.as_tensor(zn, dtype=torch.int32).contiguous().to(dev)
+        check_table_range(self.zn)
         self.n = int(self.zn.numel())
         self.dt_decay, self.seed, self.id_base = float(dt_decay), int(seed), int(id_base)
         if half_life is None or p_decay is None:

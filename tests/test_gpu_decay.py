@@ -350,3 +350,66 @@ def test_random_nuclides_walk_the_same_chains_as_the_oracle():
     got_modes = counts[:, :8].sum(0).cpu().numpy()
     assert np.array_equal(got_modes, modes)
     assert (modes[[1, 2, 3]] > 100).all() and modes[5] + modes[6] > 0     # alpha, beta-, beta+, n / p emission
+
+
+def test_random_ensemble_decay_and_force_steps_teacher_forced():
+    """Randomised differential test of the fused ensemble sub-step (decay test -> transmutation with
+    list compaction / type flips -> force -> integrate): 150 random nuclei (2..240 nucleons, random
+    Z/N, frequent decays), every sub-step compared with OracleNucleus.substep from the device's own
+    pre-step state and the same four draws."""
+    from pyqmd_b200.state import NucleusEnsemble
+    rng = np.random.default_rng(99)
+    n_nuc, steps, dt_decay, dt_phys = 150, 5, 3e9, 1 / 240
+    sizes = rng.integers(2, 241, n_nuc)
+    # proton fraction 0.3 .. 0.6: Z <= 110, and N stays >= 0 along the heuristic chains (the reference
+    # itself produces negative neutron numbers for nuclei like Z = 92, N = 0)
+    zs = np.array([int(np.clip(rng.integers(int(0.3 * a), int(0.6 * a) + 1), 1, min(a - 1, 110))) for a in sizes])
+    pos, isp, off, o = [], [], [], 0
+    for a, z in zip(sizes, zs):
+        pos.append(rng.normal(0, 1.5 * a ** (1 / 3) + 1, (a, 2)).astype(np.float32))
+        t = np.zeros(a, np.uint8); t[rng.permutation(a)[:z]] = 1
+        isp.append(t); off.append(o); o += a
+    T0 = np.array([dor.half_life(int(z), int(a - z), 0.37)[0] for a, z in zip(sizes, zs)])
+    ens = NucleusEnsemble(((zs << 16) | (sizes - zs)).astype(np.int32), np.array(off, np.int64),
+                          sizes.astype(np.int32), np.concatenate(pos), np.zeros((o, 2), np.float32),
+                          np.concatenate(isp), dt_decay=dt_decay, dt_phys=dt_phys, half_life=T0,
+                          p_decay=np.array([orc.decay_probability(t, dt_decay) for t in T0]))
+    off = np.array(off)
+    n_decays = 0
+    for s in range(steps):
+        uni = rng.random((1, n_nuc, 4))
+        cnt0, zn0 = ens.count.cpu().numpy().copy(), ens.zn.cpu().numpy().copy()
+        T_pre = ens.half_life.cpu().numpy().copy()
+        p0, v0, t0 = ens.pos.cpu().numpy().copy(), ens.vel.cpu().numpy().copy(), ens.is_proton.cpu().numpy().copy()
+        ens.step(1, uniforms=uni)
+        cnt1, zn1 = ens.count.cpu().numpy(), ens.zn.cpu().numpy()
+        p1, t1 = ens.pos.cpu().numpy(), ens.is_proton.cpu().numpy()
+        T1 = ens.half_life.cpu().numpy()
+        for k in range(n_nuc):
+            sl = slice(off[k], off[k] + cnt0[k])
+            onuc = dor.OracleNucleus(int(zn0[k]) >> 16, int(zn0[k]) & 0xffff, p0[sl, 0], p0[sl, 1], t0[sl],
+                                     v0[sl, 0], v0[sl, 1], T=float(T_pre[k]))
+            # force part from the post-decay FP32 state (teacher forced), decay part exact
+            p = orc.decay_probability(onuc.T, dt_decay)
+            if p >= 0.0 and uni[0, k, 0] < p:
+                mode, _ = onuc.decay_event(uni[0, k, 1], uni[0, k, 2], uni[0, k, 3])
+                n_decays += mode is not None
+            assert (onuc.z << 16 | onuc.n) == int(zn1[k]), (s, k)
+            assert len(onuc.x) == cnt1[k], (s, k)
+            tp = np.array([1 if q == dor.PROTON else 0 for q in onuc.types], np.uint8)
+            assert np.array_equal(t1[off[k]:off[k] + cnt1[k]], tp), (s, k)
+            assert (np.isinf(onuc.T) and np.isinf(T1[k])) or abs(T1[k] - onuc.T) <= 4e-16 * abs(onuc.T), (s, k)
+            if cnt1[k]:
+                pos32 = np.stack([onuc.x, onuc.y], 1).astype(np.float32)
+                vel32 = np.stack([onuc.vx, onuc.vy], 1).astype(np.float32)
+                ox, oy, _, _, _, _, amb = oracle_step(pos32, vel32, tp, dt_phys)
+                assert pos_error(pos32, p1[off[k]:off[k] + cnt1[k]], ox, oy, amb) <= POS_TOL, (s, k)
+    assert n_decays > 100 and int(ens.mode_counts.sum()) == n_decays
+
+
+def test_nuclides_outside_the_device_table_are_refused():
+    from pyqmd_b200.state import DecayPopulation
+    with pytest.raises(ValueError):
+        DecayPopulation(np.array([(130 << 16) | 20], np.int32), dt_decay=1.0)
+    with pytest.raises(ValueError):
+        DecayPopulation(np.array([(20 << 16) | 200], np.int32), dt_decay=1.0)
