@@ -94,3 +94,20 @@ def test_mixed_ensemble_device_layout_steps():
     assert sorted(set(cnt.tolist())) == sorted({z + n for z, n in README_ISOTOPES})
     ens.frame(4)
     assert torch.isfinite(ens.pos).all()
+
+
+def test_random_nuclides_layout_matches_reference_placement(monkeypatch):
+    """Randomised: 16 random (Z, N) with up to 90 nucleons (surplus protons, surplus neutrons, Z = 0
+    or N = 0), injected draws, against the host mirror of the reference placement."""
+    rng = np.random.default_rng(4)
+    for _ in range(16):
+        a = int(rng.integers(1, 91))
+        z = int(rng.integers(0, a + 1))
+        n = a - z
+        draws = rng.random((1, a, 21))
+        ens = NucleusEnsemble.from_device_layout(((z, n),), 1, decay=False, layout_uniforms={a: draws})
+        xy, tp = host_layout(z, n, draws[0], monkeypatch)
+        assert np.array_equal(ens.is_proton.cpu().numpy(), tp), (z, n)
+        want = xy.astype(np.float32)
+        tol = np.maximum(np.abs(want), 1e-3) * 2.0 ** -22
+        assert (np.abs(ens.pos.cpu().numpy() - want) <= tol).all(), (z, n)
