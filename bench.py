@@ -2,28 +2,38 @@
 """bench.py -- PyQMD hot path on B200: pair interactions/s (+ nucleus-steps/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload ensemble|mixed|cloud|decay] [--no-extras]
+                    [--workload cloud|ensemble|mixed|decay] [--no-extras] [--no-cpu]
 
 Contract (one JSON line from rank 0):
-  metric   "pair interactions/s" -- ordered pairs N(N-1) per nucleus-step, no Newton-3 halving
+  metric   "pair interactions/s" -- ordered pairs N(N-1) per step, no Newton-3 halving
            (nuclear_forces.py:248-251), whole job over all ranks
-  step     one sub-step (decay test -> force -> integrate, nuclear_sim.py:165-173) of the whole
-           per-GPU batch; the default workload is BASELINE.json configs[1]: 65,536 independent
-           Pb-208 nuclei per GPU, one nucleus per thread block ("weak" scaling, sharded by
-           nucleus, no data-path collective)
+  step     one Jacobi step (force -> containment -> damped Euler, nuclear_forces.py:236-323) of the
+           default workload, BASELINE.json configs[3]: ONE cloud of N = 1,000,000 nucleons (40 %
+           protons), the configuration both numeric targets of north_star are quoted on and the
+           largest single-GPU config.  "strong" scaling: the cloud is split over the ranks (i-block
+           rows of the symmetric scheme dealt to the ranks; per step an integer reduce-scatter of
+           the force accumulators + integrate + all-gather of positions, fused into ONE
+           peer-memory kernel over NVLink -- `config.exchange` says which exchange ran)
   value    device-resident throughput (state already in HBM), CUDA events, max over ranks
-  e2e      same metric through the host-buffer API: pinned host state -> H2D -> kernel -> D2H
-           every step
-  roofline dominant kernel vs the FP32 FMA peak measured in this run (FFMA-chain
-           microbenchmark; MEASURED_PEAKS.json has no FP32 figure), algorithmic FLOPs per
-           pair by SURVEY.md section 8(d)'s convention from a device-side branch census of the state
-  cpu_baseline  the oracle's C port (OpenMP, all host cores) on a bounded sample, rank 0, N=1
-  also     (unless --no-extras) the single-cloud workload of configs[3] (N = 1M nucleons,
-           i-block sharded + position all-gather, "strong" scaling) measured in the same run
+  e2e      the same metric through the host-buffer API, state in pinned HOST memory, copies inside
+           the timed region every step.  1 GPU: NuclearForces.step_cloud -> pyqmd_cloud_step_host
+           (upload, sort, step, un-sort, download -- the reference's per-step call
+           nuclear_forces.py:185-234 at N = 1M).  N GPUs: every rank uploads its block, positions
+           are all-gathered, the step runs, every rank downloads its block.
+  roofline dominant kernel (cloud_sym_kernel) vs the FP32 FMA peak measured in this run (FFMA-chain
+           microbenchmark; MEASURED_PEAKS.json has no FP32 figure), algorithmic FLOPs per ordered
+           pair by SURVEY.md section 8(d)'s convention; `frac_executed` counts only the pair
+           evaluations the kernel really executes (half: Newton's third law)
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, kind "reference") on the host cores, one
+           process per core, bounded sample; the C/OpenMP port of the oracle beside it
+  also     (unless --no-extras) every other BASELINE config in the same run -- C2 ensemble
+           (free-running AND settled state), C3 mixed, C5 decay, C1, the app frame -- each with its
+           own warm-up, >= 10 timed steps and its own clock record
+  summary  LAST key: one number per config, so that a truncated tail still carries them
 
---impl reference times the CPU port of the reference's path (the reference itself is pure
-Python and cannot travel to the GPU box; the C oracle is bit-identical to it and ~35x faster,
-i.e. a conservative baseline) with all host threads.
+--impl reference times the reference's own CPU implementation (baseline/_ref: the unmodified
+update_particles_cpu, nuclear_forces.py:236-323) on all host cores, on a bounded sample of the same
+workload (one independent sub-cloud per core).  Rank 0 only.
 """
 import argparse
 import json
@@ -38,20 +48,24 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 PB208 = (82, 126)
+README_ISO = ((1, 0), (2, 2), (6, 6), (6, 8), (26, 30), (47, 60), (79, 118), (82, 126), (92, 146))
 N_ENSEMBLE = 65536
 N_MIXED = 1_000_000
 N_CLOUD = 1_000_000
 N_DECAY = 100_000_000
+T_C14 = 180825048000.0
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "mixed", "cloud", "decay"])
+    ap.add_argument("--workload", default="cloud", choices=["cloud", "ensemble", "mixed", "decay"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (tuning runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning runs)")
     ap.add_argument("--nuclei", type=int, default=0, help="override nuclei per GPU (ensemble/mixed)")
     ap.add_argument("--cloud-n", type=int, default=N_CLOUD)
     ap.add_argument("--cloud-exchange", default="peer", choices=["peer", "nccl"],
@@ -60,6 +74,9 @@ def parse():
                     help="symmetric: every unordered pair once + integer force reduce-scatter; "
                          "ordered: i-block rows x all j, position all-gather only")
     ap.add_argument("--substeps", type=int, default=1, help="sub-steps fused per step call")
+    ap.add_argument("--isotope", default="", help="Z,N of the ensemble workload (tuning runs; default Pb-208)")
+    ap.add_argument("--settled", action="store_true",
+                    help="ensemble workload from the settled (app-faithful) state instead of free-running")
     return ap.parse_args()
 
 
@@ -103,7 +120,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def sample_once(self):
         if self.nv is not None:
@@ -140,6 +157,41 @@ def physical_gpu_index(local_rank):
 
 
 # ---------------------------------------------------------------------------------------------
+def make_cloud(n, seed=1234, frac_p=0.4, density=1 / 25):
+    """SURVEY.md section 8d: uniform disc of number density 1/25, 40 % protons, PCG64(1234)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    R = np.sqrt(n / density / np.pi)
+    r = R * np.sqrt(rng.random(n))
+    th = 2 * np.pi * rng.random(n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32)
+    isp = np.zeros(n, np.uint8)
+    isp[rng.permutation(n)[: int(round(frac_p * n))]] = 1
+    return pos, isp
+
+
+def workload_config(args):
+    """The `config` object, identical in both arms (ours / --impl reference)."""
+    g = args.gpus
+    if args.workload == "cloud":
+        return {"workload": f"C4 single 2-D nucleon cloud N={args.cloud_n} (40% protons), all-pairs "
+                            f"strong+Coulomb+Pauli, one Jacobi step per step",
+                "n_nucleons": args.cloud_n, "dt_phys": 1 / 240, "gpus": g,
+                "parallelism": f"one cloud split over {g} GPU(s) (strong scaling)"}
+    if args.workload == "ensemble":
+        return {"workload": "C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one sub-step "
+                            "(force, integrate) per step",
+                "nuclei_per_gpu": args.nuclei or N_ENSEMBLE, "dt_phys": 1 / 240, "gpus": g,
+                "parallelism": f"by nucleus over {g} GPU(s), no collective (weak scaling)"}
+    if args.workload == "mixed":
+        return {"workload": "C3 mixed ensemble of 1M nuclei over the nine preset isotopes, decay on, "
+                            "one sub-step per step", "nuclei_total": N_MIXED, "dt_phys": 1 / 240, "gpus": g,
+                "parallelism": f"by nucleus over {g} GPU(s), no collective (strong scaling)"}
+    return {"workload": "C5 decay-only Monte Carlo, 1e8 C-14 / U-238 nuclei, one should_decay per nucleus "
+                        "per step", "nuclei_total": N_DECAY, "gpus": g,
+            "parallelism": f"by nucleus over {g} GPU(s), no collective (strong scaling)"}
+
+
+# ---- CPU legs: the oracle's C port (OpenMP) and the unmodified reference (baseline/_ref) ------------
 def cpu_ensemble_sample(isotopes, n_nuclei, n_steps, threads):
     """(pairs/s, nucleus-steps/s, seconds) of the oracle port on n_nuclei template nuclei."""
     from oracle import oracle as orc
@@ -172,65 +224,73 @@ def cpu_cloud_sample(n, n_i, threads, seed=1234):
     return n_i * (n - 1) / dt, dt
 
 
-def make_cloud(n, seed=1234, frac_p=0.4, density=1 / 25):
-    """SURVEY.md section 8d: uniform disc of number density 1/25, 40 % protons, PCG64(1234)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    R = np.sqrt(n / density / np.pi)
-    r = R * np.sqrt(rng.random(n))
-    th = 2 * np.pi * rng.random(n)
-    pos = np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32)
-    isp = np.zeros(n, np.uint8)
-    isp[rng.permutation(n)[: int(round(frac_p * n))]] = 1
-    return pos, isp
+REF_SIZES = {"cloud": 640, "ensemble": 2, "mixed": 9, "decay": 400_000}
 
 
-# ---------------------------------------------------------------------------------------------
+def reference_leg(workload, steps, warmup):
+    """The unmodified reference on all host cores (baseline/ref_arm.py); None if baseline/_ref is absent."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return None
+    kind = {"cloud": "cloud", "ensemble": "ensemble", "mixed": "ensemble", "decay": "decay"}[workload]
+    iso = (PB208,) if workload == "ensemble" else README_ISO
+    r = ref_arm.run(kind, REF_SIZES[workload], steps, warmup, isotopes=iso, dt_decay=T_C14 * 1e-3)
+    what = {"cloud": f"{r['cores']} independent {REF_SIZES['cloud']}-nucleon sub-clouds (same generator and "
+                     f"density as the 1M cloud), one update_particles_cpu each per step",
+            "ensemble": f"{r['cores']} x {REF_SIZES['ensemble']} reference-built Pb-208 nuclei, should_decay + "
+                        f"update_particles_cpu each per step",
+            "mixed": f"{r['cores']} x {REF_SIZES['mixed']} reference-built nuclei over the nine preset isotopes, "
+                     f"should_decay + update_particles_cpu each per step",
+            "decay": f"{r['cores']} x {REF_SIZES['decay']} decay_chains.Nucleus.should_decay calls per step"}[workload]
+    r["sample"] = what + f"; {steps} steps, {r['seconds']:.1f} s"
+    return r
+
+
 def run_reference(args):
-    """--impl reference: the CPU port of the reference's path on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    from pyqmd_b200.state import README_ISOTOPES
-    threads = orc.max_threads()
-    if args.workload == "cloud":
-        n_i = 64 * threads
+    decay = args.workload == "decay"
+    unit = "nucleus-steps/s" if decay else "pairs/s"
+    metric = "nucleus-steps/s" if decay else "pair interactions/s"
+    r = reference_leg(args.workload, args.steps, args.warmup)
+    kind = "reference"
+    extra = {}
+    if r is None:       # baseline/_ref absent: the oracle's C port stands in (kind "port")
+        from oracle import oracle as orc
+        threads, kind = orc.max_threads(), "port"
         vals = []
         for s in range(args.warmup + args.steps):
-            v, dt = cpu_cloud_sample(65536, n_i, threads)
+            if args.workload == "cloud":
+                v, dt = cpu_cloud_sample(65536, 64 * threads, threads)
+            elif decay:
+                n_d = 1_000_000 * threads
+                un = np.random.default_rng(s).random(n_d)
+                t0 = time.perf_counter()
+                orc.decay_decisions(np.full(n_d, T_C14), T_C14 * 1e-3, un, n_threads=threads)
+                dt = time.perf_counter() - t0
+                v = n_d / dt
+            else:
+                v, _, dt = cpu_ensemble_sample((PB208,) if args.workload == "ensemble" else README_ISO,
+                                               64 * threads, 1, threads)
             if s >= args.warmup:
                 vals.append((v, dt))
-        value = float(np.mean([v for v, _ in vals]))
-        ms = float(np.mean([d for _, d in vals])) * 1e3
-        sample = f"{n_i} i-nucleons x 65,535 partners of a 65,536-nucleon PCG64(1234) cloud per step"
-        cfg = {"workload": f"C4 single 2-D nucleon cloud N={args.cloud_n} (40% protons), all-pairs, "
-                           f"i-block sharded x{args.gpus}"}
-        extra = {}
+        value, ms = float(np.mean([v for v, _ in vals])), float(np.mean([d for _, d in vals])) * 1e3
+        cores, sample = threads, "oracle C port (OpenMP), bounded sample per step; baseline/_ref not installed"
     else:
-        isotopes = README_ISOTOPES if args.workload == "mixed" else (PB208,)
-        n_nuc = 64 * threads
-        vals = []
-        for s in range(args.warmup + args.steps):
-            v, ns, dt = cpu_ensemble_sample(isotopes, n_nuc, 1, threads)
-            if s >= args.warmup:
-                vals.append((v, ns, dt))
-        value = float(np.mean([v for v, _, _ in vals]))
-        ms = float(np.mean([d for _, _, d in vals])) * 1e3
-        sample = f"{n_nuc} reference-layout nuclei x 1 sub-step per step"
-        cfg = {"workload": ("C3 mixed ensemble of 1M nuclei over the nine preset isotopes, decay on, "
-                            "sharded by nucleus" if args.workload == "mixed" else
-                            "C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one nucleus per "
-                            "thread block")}
-        extra = {"nucleus_steps_per_s": float(np.mean([n for _, n, _ in vals]))}
+        value = r["units_per_s"] if decay else r["pairs_per_s"]
+        ms, cores, sample = r["ms_per_step"], r["cores"], r["sample"]
+        if args.workload in ("ensemble", "mixed"):
+            extra["nucleus_steps_per_s"] = r["units_per_s"]
     line = {
-        "impl": "reference", "metric": "pair interactions/s", "value": value, "unit": "pairs/s",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (reference-generated initial layouts)", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak" if args.workload == "ensemble" else "strong",
+        "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     line.update(extra)
@@ -238,34 +298,65 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def timed_steps(fn, steps, warmup, dist, torch, sampler=None):
-    """W warm-up calls, then K timed calls bracketed by barrier + synchronize; CUDA events on the
-    current stream; returns seconds (max over ranks)."""
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if sampler is not None:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fn()
-    e1.record()
-    if sampler is not None:
-        sampler.sample_once()         # the queue is still draining: a sample under load even for short runs
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3
-    if dist is not None:
-        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-    return sec
+class Ctx:
+    """Everything the workload functions share."""
+
+    def __init__(self, args, torch, dist, rank, world, local_rank, lib):
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank, self.world, self.local_rank, self.lib = rank, world, local_rank, lib
+        self.dev = f"cuda:{local_rank}"
+        self.gpu_index = physical_gpu_index(local_rank)
+
+    def timed(self, fn, steps, warmup, clocks=True):
+        """W warm-up calls, then K timed calls bracketed by barrier + synchronize; CUDA events on the
+        current stream; returns (seconds as the max over ranks, clock record)."""
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(self.gpu_index) if clocks else None
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if sampler is not None:
+            sampler.sample_once()     # the queue is still draining: a sample under load even for short runs
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        if dist is not None:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec, (sampler.result() if sampler is not None else None)
+
+    def timed_wall(self, fn, steps, warmup):
+        """Same bracket for BLOCKING host-buffer calls (they synchronise internally): wall clock between
+        two device-wide synchronisations, max over ranks."""
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
 
 
 def main():
@@ -273,11 +364,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import ctypes as C
+
     import torch
     from pyqmd_b200 import _lib
-    from pyqmd_b200.state import (README_ISOTOPES, DecayPopulation, HostEnsembleRunner,
-                                  NucleonCloud, NucleusEnsemble)
-    import ctypes as C
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -288,9 +378,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    _lib.require_cuda()
     lib = _lib.lib()
-    dev = f"cuda:{local_rank}"
+    ctx = Ctx(args, torch, dist, rank, world, local_rank, lib)
     K, W = args.steps, max(args.warmup, 0)
 
     # FP32 FMA peak of this GPU, measured now (roofline denominator)
@@ -298,130 +387,63 @@ def main():
     _lib.check(lib.pyqmd_fp32_peak(4096, C.byref(f1), C.byref(f2), _lib.current_stream()), "fp32_peak")
     props = (C.c_int64 * 8)()
     lib.pyqmd_device_props(local_rank, props)
-    fp32_peak = max(f1.value, f2.value)
-    nominal = props[0] * 128 * 2 * props[3] * 1e3 / 1e12
+    ctx.fp32_peak = max(f1.value, f2.value)
+    ctx.peak_info = (f1.value, f2.value, props[0] * 128 * 2 * props[3] * 1e3 / 1e12)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    ctx.hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ctx.hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
-    sampler = ClockSampler(physical_gpu_index(local_rank))
     line = {"metric": "pair interactions/s", "unit": "pairs/s", "n_gpus": world, "steps": K,
             "warmup": W, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic"}
-    launches = 0
+    fn = {"cloud": bench_cloud, "ensemble": bench_ensemble, "mixed": bench_ensemble, "decay": bench_decay}[
+        args.workload]
+    res = fn(ctx, args.workload, K, W, with_e2e=not args.no_e2e)
+    details = dict(res.pop("config", {}), **res.pop("details", {}))
+    details.pop("workload", None)
+    line.update(res)
+    line["config"] = dict(workload_config(args), **details)
 
-    ens = tot_nuc = tot_pairs = None
-    if args.workload in ("ensemble", "mixed"):
-        res, ens, tot_nuc, tot_pairs = bench_ensemble(args, args.workload, K, W, rank, world, dev, dist,
-                                                      torch, sampler, fp32_peak,
-                                                      (f1.value, f2.value, nominal), hbm_peak, hbm_src,
-                                                      with_e2e=True)
-        line.update(res)
-        clocks = sampler.result()
-        launches = K * len(ens.bins)
-    elif args.workload == "cloud":
-        line.update(bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak,
-                                (f1.value, f2.value, nominal)))
-        clocks = sampler.result()
-        launches = K * 4
-    else:
-        line.update(bench_decay(args, K, W, rank, world, dev, dist, torch, sampler, hbm_peak, hbm_src))
-        clocks = sampler.result()
-        launches = K
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.workload)
 
-    line["clocks"] = clocks
-    line["gpu_launches"] = launches
-
-    if rank == 0 and world == 1:
-        from oracle import oracle as orc
-        threads = orc.max_threads()
-        if args.workload == "cloud":
-            v, dt = cpu_cloud_sample(65536, 4096 * threads, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "sample": f"{min(4096 * threads, 65536)} i-nucleons of a 65,536-nucleon cloud, "
-                                              f"{dt:.1f} s"}
-        elif args.workload in ("ensemble", "mixed"):
-            isotopes = (PB208,) if args.workload == "ensemble" else README_ISOTOPES
-            n_s = 256 * threads
-            v, ns, dt = cpu_ensemble_sample(isotopes, n_s, 30, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "nucleus_steps_per_s": ns,
-                                    "sample": f"{n_s} nuclei x 30 sub-steps of the same workload, "
-                                              f"{dt:.1f} s, OpenMP over nuclei"}
-
-    if not args.no_extras and args.workload == "ensemble":
-        # every other config of BASELINE.json in the same line; a failure here must not cost the headline
+    summary = {args.workload: line["value"], "e2e": (line.get("e2e") or {}).get("value"),
+               "roofline_frac": line["roofline"]["frac"]}
+    if not args.no_extras and args.workload == "cloud":
+        also = {}
+        for name, f, wl, k, w in (("ensemble_c2", bench_ensemble, "ensemble", 20, 5),
+                                  ("ensemble_c2_settled", bench_ensemble_settled, "ensemble", 10, 3),
+                                  ("mixed_c3", bench_ensemble, "mixed", 10, 3),
+                                  ("decay_c5", bench_decay, "decay", 10, 3)):
+            try:        # a failure here must not cost the headline
+                r = f(ctx, wl, k, w, with_e2e=(name == "ensemble_c2"))
+                r["steps"], r["warmup"] = k, w
+                also[name] = r
+                summary[name] = r["value"]
+                summary[name + "_frac"] = r["roofline"]["frac"]
+                if "e2e" in r:
+                    summary[name + "_e2e"] = r["e2e"]["value"]
+                torch.cuda.empty_cache()
+            except Exception as exc:      # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                also[name] = {"error": repr(exc)[:300]}
         try:
-            # app-faithful frame (nuclear_sim.py:161-176): 4 sub-steps, then the overlap projection, from a
-            # settled state (fresh layouts + 12 frames; the step-only state above has collapsed)
-            from pyqmd_b200.state import NucleusEnsemble
-            n_f = ens.n_nuclei
-            del ens
-            torch.cuda.empty_cache()
-            ens = NucleusEnsemble.from_templates((PB208,), n_f, device=dev, id_base=rank * n_f, decay=False)
-            for _ in range(12):
-                ens.frame(4)
-            p0 = int(ens.push_count.item())
-            sec_f = timed_steps(lambda: ens.frame(4), 10, 1, dist, torch)
-            pushes = (int(ens.push_count.item()) - p0) / 11 / n_f
-            sec_s = timed_steps(lambda: ens.step(4), 10, 1, dist, torch)
-            census_f, flops_f = ens.census(range(0, n_f, max(1, n_f // 256)))
-            frame = {"ms_per_frame": sec_f / 10 * 1e3, "substeps_per_frame": 4,
-                     "ms_4_substeps_alone": sec_s / 10 * 1e3,
-                     "nucleus_frames_per_s": float(tot_nuc.item()) * 10 / sec_f,
-                     "pairs_per_s": float(tot_pairs.item()) / args.substeps * 4 * 10 / sec_f,
-                     "pushes_per_nucleus_frame": pushes, "flops_per_pair": flops_f,
-                     "branch_census": census_f,
-                     "note": "4 sub-steps + resolve_overlaps per frame, device resident, settled nuclei"}
-            del ens
-            torch.cuda.empty_cache()
-            keep = ("metric", "unit", "value", "ms_per_step", "config", "roofline", "scaling",
-                    "nucleus_steps_per_s", "decays")
-            also = {"frame": frame}
-            extra = bench_cloud(args, 2, 1, rank, world, dev, dist, torch, None, fp32_peak,
-                                (f1.value, f2.value, nominal))
-            also["cloud"] = {k: extra[k] for k in keep if k in extra}
-            torch.cuda.empty_cache()
-            extra, ens3, _, _ = bench_ensemble(args, "mixed", 5, 3, rank, world, dev, dist, torch, None,
-                                               fp32_peak, (f1.value, f2.value, nominal), hbm_peak, hbm_src,
-                                               with_e2e=False)
-            also["mixed"] = {k: extra[k] for k in keep if k in extra}
-            del ens3
-            torch.cuda.empty_cache()
-            extra = bench_decay(args, 3, 3, rank, world, dev, dist, torch, None, hbm_peak, hbm_src)
-            also["decay"] = {k: extra[k] for k in keep if k in extra}
-            torch.cuda.empty_cache()
             if rank == 0:
-                also["c1"] = bench_c1(dev, torch)
-            if rank == 0 and world == 1:
-                # the reference's CPU path (C port, all host threads) beside each config
-                from oracle import oracle as orc
-                threads = orc.max_threads()
-                v, dt_s = cpu_cloud_sample(65536, 1024 * threads, threads)
-                also["cloud"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                                 "sample": f"{1024 * threads} i-nucleons x 65,535 partners, {dt_s:.1f} s"}
-                v, ns, dt_s = cpu_ensemble_sample(README_ISOTOPES, 9 * 32 * threads, 10, threads)
-                also["mixed"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "nucleus_steps_per_s": ns,
-                                                 "cores": threads, "kind": "port",
-                                                 "sample": f"{9 * 32 * threads} nuclei x 10 sub-steps, {dt_s:.1f} s"}
-                n_d = 4_000_000 * threads
-                Tn = np.full(n_d, 180825048000.0)
-                un = np.random.default_rng(1).random(n_d)
-                t0 = time.perf_counter()
-                orc.decay_decisions(Tn, 180825048000.0 * 1e-3, un, n_threads=threads)
-                dt_s = time.perf_counter() - t0
-                also["decay"]["cpu_baseline"] = {"value": n_d / dt_s, "unit": "nucleus-steps/s", "cores": threads,
-                                                 "kind": "port",
-                                                 "sample": f"{n_d} should_decay decisions with supplied uniforms, {dt_s:.2f} s"}
-            line["also"] = also
+                also["c1"] = bench_c1(ctx)
+                summary["c1_ms_per_1000_substeps_resident"] = also["c1"]["device_resident_1000"]["ms_total"]
         except Exception as exc:      # noqa: BLE001
-            import traceback
-            traceback.print_exc()
-            line.setdefault("also", {})["error"] = repr(exc)[:300]
+            also["c1"] = {"error": repr(exc)[:300]}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            for name, wl in (("ensemble_c2", "ensemble"), ("mixed_c3", "mixed"), ("decay_c5", "decay")):
+                if name in also and "error" not in also[name]:
+                    also[name]["cpu_baseline"] = cpu_baseline(wl, short=True)
+        line["also"] = also
+    line["summary"] = summary
 
     if rank == 0:
         print(json.dumps(line))
@@ -429,90 +451,244 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_ensemble(args, workload, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, peak_info,
-                   hbm_peak, hbm_src, with_e2e):
-    """C2 (``ensemble``: 65,536 Pb-208 per GPU, weak) or C3 (``mixed``: 1M nuclei over the nine
-    preset isotopes in total, decay on, strong)."""
+def cpu_baseline(workload, short=False):
+    """The reference's CPU path beside the GPU number: the unmodified reference (kind "reference",
+    baseline/_ref) and the oracle's C/OpenMP port, both on all host cores, bounded samples."""
+    from oracle import oracle as orc
+    threads = orc.max_threads()
+    decay = workload == "decay"
+    unit = "nucleus-steps/s" if decay else "pairs/s"
+    if workload == "cloud":
+        n_i = (1024 if short else 4096) * threads
+        v, dt = cpu_cloud_sample(65536, n_i, threads)
+        port = {"value": v, "sample": f"{min(n_i, 65536)} i-nucleons x 65,535 partners, {dt:.1f} s"}
+    elif decay:
+        n_d = 4_000_000 * threads
+        un = np.random.default_rng(1).random(n_d)
+        t0 = time.perf_counter()
+        orc.decay_decisions(np.full(n_d, T_C14), T_C14 * 1e-3, un, n_threads=threads)
+        dt = time.perf_counter() - t0
+        port = {"value": n_d / dt, "sample": f"{n_d} should_decay decisions with supplied uniforms, {dt:.2f} s"}
+    else:
+        iso = (PB208,) if workload == "ensemble" else README_ISO
+        n_s, n_st = (64 if short else 256) * threads, (10 if short else 30)
+        v, ns, dt = cpu_ensemble_sample(iso, n_s, n_st, threads)
+        port = {"value": v, "nucleus_steps_per_s": ns,
+                "sample": f"{n_s} nuclei x {n_st} sub-steps, {dt:.1f} s, OpenMP over nuclei"}
+    port.update(unit=unit, cores=threads, kind="port")
+    ref = None
+    try:
+        ref = reference_leg(workload, 3 if short else 8, 1)
+    except Exception as exc:      # noqa: BLE001
+        port["reference_error"] = repr(exc)[:200]
+    if ref is None:
+        return port
+    out = {"value": ref["units_per_s"] if decay else ref["pairs_per_s"], "unit": unit, "cores": ref["cores"],
+           "kind": "reference", "sample": ref["sample"], "port": port}
+    if workload in ("ensemble", "mixed"):
+        out["nucleus_steps_per_s"] = ref["units_per_s"]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def bench_cloud(ctx, workload, K, W, with_e2e=True):
+    """C4: one cloud of N nucleons, strong scaling."""
+    from pyqmd_b200.forces import NuclearForces
+    from pyqmd_b200.state import NucleonCloud
+    args, torch = ctx.args, ctx.torch
+    n = args.cloud_n
+    pos, isp = make_cloud(n)
+    cloud = NucleonCloud(pos, isp, device=ctx.dev, rank=ctx.rank, world=ctx.world, scheme=args.cloud_scheme,
+                         exchange=args.cloud_exchange)
+    sec, clocks = ctx.timed(lambda: cloud.step(1), K, W)
+    pairs = float(n) * (n - 1)
+    f_pp = (float(isp.sum()) / n) ** 2
+    flops_pair = 23.0 + 3.0 * f_pp
+    mine = cloud.pairs_per_step() * K / sec
+    sym = args.cloud_scheme == "symmetric"
+    kernel = "cloud_sym_kernel" if sym else "cloud_force_kernel"
+    achieved = mine * flops_pair / 1e12
+    res = {
+        "value": pairs * K / sec, "ms_per_step": sec / K * 1e3, "scaling": "strong",
+        "details": {"l2_policy": "per-step working set (positions 8N B + accumulators 16N B) is L2 resident "
+                                 "by design; compute bound",
+                    "scheme": args.cloud_scheme, "exchange": cloud.exchange,
+                    "exchange_detail": ("integer force reduce-scatter + integrate + position all-gather "
+                                        + ("fused in one peer-memory kernel (NVLink/NVSwitch, symmetric memory)"
+                                           if cloud.exchange == "peer" else "via NCCL")
+                                        if sym and ctx.world > 1 else
+                                        ("none (1 GPU)" if ctx.world == 1 else "NCCL position all-gather"))},
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": ctx.fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / ctx.fp32_peak,
+                     "frac_executed": achieved / ctx.fp32_peak * (0.5 if sym else 1.0),
+                     "traffic": ncu_traffic(kernel) if n == N_CLOUD and ctx.world == 1 else None,
+                     "kernel": kernel, "flops_per_pair": flops_pair,
+                     "algorithmic_bytes_per_launch": 36 * n,
+                     "executed_pair_evaluations_per_step": pairs / 2 if sym else pairs,
+                     "note": ("algorithmic FLOPs of all N(N-1) ordered pairs (SURVEY 8d) over the kernel time; "
+                              "the symmetric scheme evaluates each unordered pair once, so `frac` may exceed 1 "
+                              "and `frac_executed` (half) is the pipe utilisation; the kernel's own bound is "
+                              "the MUFU pipe, 2 per unordered pair at 16/clk/SM"
+                              if sym else "ordered pairs, each evaluated"),
+                     "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, f32x2 %.1f "
+                                    "TFLOP/s); nominal %.1f" % ctx.peak_info},
+        "clocks": clocks, "gpu_launches": K * 4,
+    }
+    if with_e2e:
+        k2, w2 = max(3, K // 2), 2
+        if ctx.world == 1:
+            # the reference-shaped call: host arrays in, host arrays out, caller's order, one C-ABI call
+            pin = lambda a: torch.from_numpy(a).pin_memory()
+            h_pos, h_vel, h_isp = pin(pos.copy()), pin(np.zeros_like(pos)), pin(isp.copy())
+            nf = NuclearForces()
+            sec_e = ctx.timed_wall(lambda: nf.step_cloud(h_pos, h_vel, h_isp, 1 / 240, 1), k2, w2)
+            h2d, d2h = 8 * n + 8 * n + n, 16 * n
+            api = "NuclearForces.step_cloud -> pyqmd_cloud_step_host (upload, sort, step, un-sort, download)"
+        else:
+            blk = cloud.i1 - cloud.i0
+            h_pos = torch.empty(blk, 2, dtype=torch.float32).pin_memory()
+            h_vel = torch.empty(blk, 2, dtype=torch.float32).pin_memory()
+            cloud.download_block(h_pos, h_vel)
+            sec_e = ctx.timed_wall(lambda: cloud.step_host(h_pos, h_vel), k2, w2)
+            h2d, d2h = 16 * blk, 16 * blk
+            api = ("NucleonCloud.step_host: every rank uploads its block (pos, vel), positions are "
+                   "all-gathered, the step runs, every rank downloads its block")
+        res["e2e"] = {"value": pairs * k2 / sec_e, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": sec_e / k2 * 1e3, "steps": k2, "api": api,
+                      "timing": "wall clock between device-wide synchronisations (the call blocks), max over ranks"}
+    del cloud
+    torch.cuda.empty_cache()
+    return res
+
+
+def _ensemble_result(ctx, workload, ens, K, sec, clocks, flops_pair, census, substeps, isotopes):
+    torch, dist = ctx.torch, ctx.dist
+    pairs_step = ens.pairs_per_step() * substeps
+    nucleons = int(ens.count.sum().item())
+    tot_pairs = torch.tensor([float(pairs_step)], device=ctx.dev, dtype=torch.float64)
+    tot_nuc = torch.tensor([float(ens.n_nuclei)], device=ctx.dev, dtype=torch.float64)
+    decays = ens.mode_counts.clone()
+    if dist is not None:
+        dist.all_reduce(tot_pairs); dist.all_reduce(tot_nuc); dist.all_reduce(decays)
+    my_rate = pairs_step * K / sec
+    achieved = my_rate * flops_pair / 1e12
+    res = {
+        "metric": "pair interactions/s", "unit": "pairs/s",
+        "value": float(tot_pairs.item()) * K / sec, "ms_per_step": sec / K * 1e3,
+        "scaling": "weak" if workload == "ensemble" and not ctx.args.nuclei else "strong",
+        "config": {"workload": ("C2 ensemble of 65,536 independent Pb-208 nuclei per GPU"
+                                if workload == "ensemble" and isotopes == (PB208,) else
+                                "C3 mixed ensemble of 1M nuclei over the nine preset isotopes, decay on, "
+                                "sharded by nucleus" if workload == "mixed" else f"ensemble of {isotopes}"),
+                   "nuclei_total": int(tot_nuc.item()), "nucleons_per_gpu": nucleons,
+                   "substeps_per_step": substeps, "dt_phys": 1 / 240,
+                   "l2_policy": "inputs larger than L2 (state %.0f MB per GPU)" % (nucleons * 17 / 1e6),
+                   "parallelism": f"by-nucleus x{ctx.world}, no collective"},
+        "nucleus_steps_per_s": float(tot_nuc.item()) * substeps * K / sec,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": ctx.fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / ctx.fp32_peak,
+                     "traffic": ncu_traffic("ensemble_kernel") if workload == "ensemble"
+                     and not ctx.args.nuclei and substeps == 1 else None,
+                     "kernel": "ensemble kernel (see DESIGN.md section 4)", "flops_per_pair": flops_pair,
+                     "algorithmic_bytes_per_launch": 36 * nucleons, "branch_census_end": census,
+                     "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
+                                    "f32x2 %.1f TFLOP/s); nominal %.1f" % ctx.peak_info,
+                     "hbm_gbs": nucleons * 36 * K / sec / 1e9, "hbm_peak_gbs": ctx.hbm_peak,
+                     "hbm_peak_source": ctx.hbm_src},
+        "clocks": clocks, "gpu_launches": K * len(ens.bins),
+    }
+    if ens.decay:
+        res["decays"] = {"total_events": int(decays.sum().item()), "by_mode": [int(v) for v in decays.tolist()]}
+    return res, tot_pairs
+
+
+def bench_ensemble(ctx, workload, K, W, with_e2e=True):
+    """C2 (``ensemble``: 65,536 Pb-208 per GPU, weak) or C3 (``mixed``: 1M nuclei over the nine preset
+    isotopes in total, decay on, strong).  Free-running sub-steps (no overlap projection): the state the
+    reference's own un-projected dynamics collapse into."""
+    import math
+
     from pyqmd_b200.state import README_ISOTOPES, HostEnsembleRunner, NucleusEnsemble
+    args = ctx.args
     isotopes = (PB208,) if workload == "ensemble" else README_ISOTOPES
-    total = args.nuclei * world if args.nuclei else (N_ENSEMBLE * world if workload == "ensemble"
-                                                     else N_MIXED)
-    per = (total + world - 1) // world
-    lo = rank * per
+    if workload == "ensemble" and args.isotope:
+        isotopes = (tuple(int(v) for v in args.isotope.split(",")),)
+    total = args.nuclei * ctx.world if args.nuclei else (N_ENSEMBLE * ctx.world if workload == "ensemble"
+                                                         else N_MIXED)
+    per = (total + ctx.world - 1) // ctx.world
+    lo = ctx.rank * per
     n_mine = max(0, min(per, total - lo))
     decay = workload == "mixed"
-    ens = NucleusEnsemble.from_templates(isotopes, n_mine, device=dev, id_base=lo, decay=decay,
-                                         dt_decay=180825048000.0 * 1e-3, seed=2024)
-    pairs_step = ens.pairs_per_step() * args.substeps
-    nucleons = int(ens.count.sum().item())
-    import math
+    ens = NucleusEnsemble.from_templates(isotopes, n_mine, device=ctx.dev, id_base=lo, decay=decay,
+                                         dt_decay=T_C14 * 1e-3, seed=2024)
     stride = max(1, ens.n_nuclei // 256)
     while math.gcd(stride, len(isotopes)) != 1:      # isotopes cycle with the nucleus id: hit them all
         stride += 1
     sample = range(0, ens.n_nuclei, stride)
+    if args.settled and workload == "ensemble":
+        for _ in range(12):
+            ens.frame(4)
     flops0 = ens.census(sample)[1]
-    sec = timed_steps(lambda: ens.step(args.substeps), K, W, dist, torch, sampler)
+    sec, clocks = ctx.timed(lambda: ens.step(args.substeps), K, W)
     census1, flops1 = ens.census(sample)
-    tot_pairs = torch.tensor([float(pairs_step)], device=dev, dtype=torch.float64)
-    tot_nuc = torch.tensor([float(ens.n_nuclei)], device=dev, dtype=torch.float64)
-    decays = ens.mode_counts.clone()
-    if dist is not None:
-        dist.all_reduce(tot_pairs); dist.all_reduce(tot_nuc); dist.all_reduce(decays)
-    value = float(tot_pairs.item()) * K / sec
-    flops_pair = 0.5 * (flops0 + flops1)
-    my_rate = pairs_step * K / sec          # this rank's kernel
-    res = {
-        "value": value, "ms_per_step": sec / K * 1e3,
-        "scaling": "weak" if workload == "ensemble" and not args.nuclei else "strong",
-        "config": {"workload": ("C2 ensemble of 65,536 independent Pb-208 nuclei per GPU, one "
-                                "nucleus per thread block" if workload == "ensemble" else
-                                "C3 mixed ensemble of 1M nuclei over the nine preset isotopes, "
-                                "decay on, sharded by nucleus"),
-                   "nuclei_total": int(tot_nuc.item()), "nucleons_per_gpu": nucleons,
-                   "substeps_per_step": args.substeps, "dt_phys": 1 / 240,
-                   "l2_policy": "inputs larger than L2 (state %.0f MB per GPU)" % (nucleons * 17 / 1e6),
-                   "parallelism": f"by-nucleus x{world}, no collective"},
-        "nucleus_steps_per_s": float(tot_nuc.item()) * args.substeps * K / sec,
-        "roofline": {"bound": "fp32", "achieved": my_rate * flops_pair / 1e12, "peak": fp32_peak,
-                     "unit": "TFLOP/s", "frac": my_rate * flops_pair / 1e12 / fp32_peak,
-                     "traffic": ncu_traffic("ensemble_pair_kernel") if workload == "ensemble"
-                     and not args.nuclei and args.substeps == 1 else None,
-                     "kernel": "ensemble_pair_kernel",
-                     "flops_per_pair": flops_pair, "branch_census_end": census1,
-                     "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
-                                    "f32x2 %.1f TFLOP/s); nominal %.1f" % peak_info,
-                     "hbm_gbs": nucleons * 36 * args.substeps * K / sec / 1e9 / max(args.substeps, 1),
-                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
-    }
-    if decay:
-        res["decays"] = {"total_events": int(decays.sum().item()),
-                         "by_mode": [int(v) for v in decays.tolist()]}
+    res, tot_pairs = _ensemble_result(ctx, workload, ens, K, sec, clocks, 0.5 * (flops0 + flops1), census1,
+                                      args.substeps, isotopes)
+    res["state"] = ("settled (12 app frames), then free-running" if args.settled else
+                    "free-running sub-steps from the reference layout (collapses, SURVEY section 7)")
     if with_e2e:
         # e2e: host-buffer API, H2D + kernel + D2H every step
-        runner = HostEnsembleRunner(ens, chunks=8)
+        runner = HostEnsembleRunner(ens, chunks=16)
         k2 = max(3, K // 4)
-        sec_e2e = timed_steps(lambda: runner.step(args.substeps), k2, 2, dist, torch)
+        sec_e2e, _ = ctx.timed(lambda: runner.step(args.substeps), k2, 2, clocks=False)
         res["e2e"] = {"value": float(tot_pairs.item()) * k2 / sec_e2e, "unit": "pairs/s",
                       "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
-                      "chunks": runner.n_chunks}
-        # for information: one host round trip per app frame (4 sub-steps, nuclear_sim.py:153) instead of
-        # one per sub-step -- what NuclearForces.step(particles, dt, n) offers over the reference's call
-        sec_e2e4 = timed_steps(lambda: runner.step(4 * args.substeps), max(3, k2 // 4), 1, dist, torch)
+                      "chunks": runner.n_chunks, "api": "HostEnsembleRunner.step -> pyqmd_ensemble_step_host"}
+        sec_e2e4, _ = ctx.timed(lambda: runner.step(4 * args.substeps), max(3, k2 // 4), 1, clocks=False)
         res["e2e"]["value_4_substeps_per_call"] = (float(tot_pairs.item()) * 4 * max(3, k2 // 4) / sec_e2e4)
         del runner
-    return res, ens, tot_nuc, tot_pairs
+    del ens
+    ctx.torch.cuda.empty_cache()
+    return res
 
 
-def bench_c1(dev, torch):
+def bench_ensemble_settled(ctx, workload, K, W, with_e2e=False):
+    """C2 from the SETTLED, app-faithful state: fresh layouts + 12 app frames (4 sub-steps + the overlap
+    projection, nuclear_sim.py:161-176); then (a) K app frames, (b) K calls of 4 sub-steps alone -- the
+    roofline of the same kernel on a physical state (94 % tail pairs instead of 98 % hard core)."""
+    from pyqmd_b200.state import NucleusEnsemble
+    n_f = (ctx.args.nuclei or N_ENSEMBLE)
+    ens = NucleusEnsemble.from_templates((PB208,), n_f, device=ctx.dev, id_base=ctx.rank * n_f, decay=False)
+    for _ in range(12):
+        ens.frame(4)
+    sample = range(0, n_f, max(1, n_f // 256))
+    p0 = int(ens.push_count.item())
+    sec_f, clocks_f = ctx.timed(lambda: ens.frame(4), K, W)
+    pushes = (int(ens.push_count.item()) - p0) / (K + W) / n_f
+    census0, flops0 = ens.census(sample)
+    sec_s, clocks = ctx.timed(lambda: ens.step(4), K, 1)
+    census1, flops1 = ens.census(sample)
+    res, tot_pairs = _ensemble_result(ctx, "ensemble", ens, K, sec_s, clocks, 0.5 * (flops0 + flops1), census1, 4,
+                                      (PB208,))
+    res["state"] = "settled: 12 app frames (4 sub-steps + resolve_overlaps) from the reference layout"
+    res["frame"] = {"ms_per_frame": sec_f / K * 1e3, "substeps_per_frame": 4,
+                    "pairs_per_s": float(tot_pairs.item()) * K / sec_f,
+                    "pushes_per_nucleus_frame": pushes, "clocks": clocks_f,
+                    "note": "4 sub-steps + resolve_overlaps per frame (nuclear_sim.py:161-176), device resident"}
+    del ens
+    ctx.torch.cuda.empty_cache()
+    return res
+
+
+def bench_c1(ctx):
     """C1: one U-238 nucleus (configs[0]), 1000 force+integrate(+decay test) steps.
     (a) through the reference-shaped drop-in NuclearForces.update_particles_cpu(list[Particle], dt),
         one host round trip per sub-step, exactly how nuclear_sim.py:171-173 calls it;
     (b) the same 1000 sub-steps fused into one call (NuclearForces.step);
     (c) device resident (NucleusEnsemble of one nucleus, 1000 sub-steps in one launch, decay on)."""
-    import random
     from pyqmd_b200.forces import NuclearForces
     from pyqmd_b200.state import NucleusEnsemble, layout_templates
     from pyqmd_b200.types import Particle, ParticleType
+    torch = ctx.torch
     tm = layout_templates()
     xy, isp = tm["z92_n146_xy"][0], tm["z92_n146_isp"][0]
     mk = lambda: [Particle(400.0 + float(x), 400.0 + float(y),
@@ -532,7 +708,7 @@ def bench_c1(dev, torch):
     t0 = time.perf_counter()
     nf.step(ps, 1 / 240, 1000)
     fused = time.perf_counter() - t0
-    ens = NucleusEnsemble.from_templates(((92, 146),), 1, device=dev, decay=True,
+    ens = NucleusEnsemble.from_templates(((92, 146),), 1, device=ctx.dev, decay=True,
                                          dt_decay=1.409993568e17 * 1e-3, seed=1)
     ens.step(10)
     torch.cuda.synchronize()
@@ -542,85 +718,73 @@ def bench_c1(dev, torch):
     e1.record()
     torch.cuda.synchronize()
     resident = e0.elapsed_time(e1) * 1e-3
-    from oracle import oracle as orc
-    x, y = xy[:, 0].astype(np.float64), xy[:, 1].astype(np.float64)
-    t0 = time.perf_counter()
-    orc.ensemble_force_steps(np.array([0], np.int64), np.array([238], np.int32), x, y, np.zeros(238),
-                             np.zeros(238), isp, 1 / 240, 200, n_threads=1)
-    cpu = (time.perf_counter() - t0) / 200
-    return {"config": {"workload": "C1 single U-238 nucleus (238 nucleons), 1000 sub-steps"},
-            "cpu_port_1core": {"ms_per_substep": cpu * 1e3, "pairs_per_s": pairs / cpu,
-                               "note": "C oracle port, one core (one nucleus does not parallelise)"},
-            "dropin_per_substep_call": {"ms_per_call": per_call * 1e3, "pairs_per_s": pairs / per_call,
-                                        "api": "NuclearForces.update_particles_cpu(list[Particle], dt)"},
-            "dropin_fused_1000": {"ms_total": fused * 1e3, "pairs_per_s": pairs * 1000 / fused,
-                                  "api": "NuclearForces.step(list[Particle], dt, 1000)"},
-            "device_resident_1000": {"ms_total": resident * 1e3, "pairs_per_s": pairs * 1000 / resident,
-                                     "nucleus_steps_per_s": 1000 / resident,
-                                     "api": "NucleusEnsemble.step(1000), decay test on"},
-            "reference_python_cpu": "75-91 ms per sub-step (SURVEY.md section 6 [probe]), 6.2-7.5e5 pairs/s"}
+    out = {"config": {"workload": "C1 single U-238 nucleus (238 nucleons), 1000 sub-steps"},
+           "dropin_per_substep_call": {"ms_per_call": per_call * 1e3, "pairs_per_s": pairs / per_call,
+                                       "api": "NuclearForces.update_particles_cpu(list[Particle], dt)"},
+           "dropin_fused_1000": {"ms_total": fused * 1e3, "pairs_per_s": pairs * 1000 / fused,
+                                 "api": "NuclearForces.step(list[Particle], dt, 1000)"},
+           "device_resident_1000": {"ms_total": resident * 1e3, "pairs_per_s": pairs * 1000 / resident,
+                                    "nucleus_steps_per_s": 1000 / resident,
+                                    "api": "NucleusEnsemble.step(1000), decay test on"}}
+    if not ctx.args.no_cpu and ctx.world == 1:
+        from oracle import oracle as orc
+        x, y = xy[:, 0].astype(np.float64), xy[:, 1].astype(np.float64)
+        t0 = time.perf_counter()
+        orc.ensemble_force_steps(np.array([0], np.int64), np.array([238], np.int32), x, y, np.zeros(238),
+                                 np.zeros(238), isp, 1 / 240, 200, n_threads=1)
+        cpu = (time.perf_counter() - t0) / 200
+        out["cpu_port_1core"] = {"ms_per_substep": cpu * 1e3, "pairs_per_s": pairs / cpu,
+                                 "note": "C oracle port, one core (one nucleus does not parallelise)"}
+        try:    # the unmodified reference on this box: the same U-238, 3 sub-steps, one core
+            from oracle import ref_loader
+            if ref_loader.available():
+                R = ref_loader.Ref()
+                rp = R.make_particles(400.0 + x, 400.0 + y, np.zeros(238), np.zeros(238), isp)
+                rf = R.forces()
+                rf.update_particles_cpu(rp, 1 / 240)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    rf.update_particles_cpu(rp, 1 / 240)
+                ref = (time.perf_counter() - t0) / 3
+                out["reference_python_1core"] = {"ms_per_substep": ref * 1e3, "pairs_per_s": pairs / ref,
+                                                 "kind": "reference",
+                                                 "note": "unmodified update_particles_cpu (baseline/_ref), this box"}
+        except Exception as exc:      # noqa: BLE001
+            out["reference_python_1core"] = {"error": repr(exc)[:200]}
+    return out
 
 
-def bench_cloud(args, K, W, rank, world, dev, dist, torch, sampler, fp32_peak, peak_info):
-    from pyqmd_b200.state import NucleonCloud
-    n = args.cloud_n
-    pos, isp = make_cloud(n)
-    cloud = NucleonCloud(pos, isp, device=dev, rank=rank, world=world, scheme=args.cloud_scheme,
-                         exchange=args.cloud_exchange)
-    sec = timed_steps(lambda: cloud.step(1), K, W, dist, torch, sampler)
-    pairs = float(n) * (n - 1)
-    f_pp = (float(isp.sum()) / n) ** 2
-    flops_pair = 23.0 + 3.0 * f_pp
-    mine = cloud.pairs_per_step() * K / sec
-    return {
-        "value": pairs * K / sec, "ms_per_step": sec / K * 1e3, "scaling": "strong",
-        "config": {"workload": f"C4 single 2-D nucleon cloud N={n} (40% protons), all-pairs, "
-                               f"i-block sharded x{world}",
-                   "l2_policy": "per-step working set (positions 8N B) is L2 resident by design; "
-                                "compute bound", "dt_phys": 1 / 240,
-                   "scheme": args.cloud_scheme, "exchange": cloud.exchange,
-                   "parallelism": (f"i-block rows dealt x{world}; integer force reduce-scatter + integrate + "
-                                   f"position all-gather " + ("fused in one peer-memory kernel (NVLink)"
-                                                              if cloud.exchange == "peer" else "via NCCL")
-                                   if args.cloud_scheme == "symmetric" and world > 1 else
-                                   f"i-block x{world}" + (" + NCCL position all-gather" if world > 1 else ""))},
-        "roofline": {"bound": "fp32", "achieved": mine * flops_pair / 1e12, "peak": fp32_peak,
-                     "unit": "TFLOP/s", "frac": mine * flops_pair / 1e12 / fp32_peak,
-                     "traffic": None,   # ncu capture is at N = 262,144 (profiles/traffic.json): 6.9 MB per launch
-                     "kernel": "cloud_sym_kernel" if args.cloud_scheme == "symmetric" else "cloud_force_kernel",
-                     "flops_per_pair": flops_pair,
-                     "executed_pair_evaluations_per_step": pairs / 2 if args.cloud_scheme == "symmetric" else pairs,
-                     "note": ("algorithmic FLOPs of all N(N-1) ordered pairs (SURVEY 8d) over time; the "
-                              "symmetric scheme evaluates each unordered pair once, so frac may exceed 1"
-                              if args.cloud_scheme == "symmetric" else "ordered pairs, each evaluated"),
-                     "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, f32x2 %.1f "
-                                    "TFLOP/s); nominal %.1f" % peak_info},
-    }
-
-
-def bench_decay(args, K, W, rank, world, dev, dist, torch, sampler, hbm_peak, hbm_src):
+def bench_decay(ctx, workload, K, W, with_e2e=False):
     from pyqmd_b200.state import DecayPopulation
+    torch = ctx.torch
     total = N_DECAY
-    per = (total + world - 1) // world
-    lo = rank * per
+    per = (total + ctx.world - 1) // ctx.world
+    lo = ctx.rank * per
     n_mine = max(0, min(per, total - lo))
     zn = torch.full((n_mine,), (6 << 16) | 8, dtype=torch.int32)
     zn[n_mine // 2:] = (92 << 16) | 146
-    pop = DecayPopulation(zn, device=dev, dt_decay=180825048000.0 * 1e-3, seed=7, id_base=lo,
+    pop = DecayPopulation(zn, device=ctx.dev, dt_decay=T_C14 * 1e-3, seed=7, id_base=lo,
                           watch=((6, 8), (92, 146)))
-    sub = max(args.substeps, 1)
-    sec = timed_steps(lambda: pop.step(sub), K, W, dist, torch, sampler)
-    return {
+    sub = max(ctx.args.substeps, 1)
+    sec, clocks = ctx.timed(lambda: pop.step(sub), K, W)
+    bytes_nuc, note = pop.bytes_per_nucleus_launch()
+    res = {
         "metric": "nucleus-steps/s", "unit": "nucleus-steps/s", "value": float(total) * sub * K / sec,
         "ms_per_step": sec / K * 1e3, "scaling": "strong", "dtype": "f64",
         "config": {"workload": "C5 decay-only Monte Carlo, 1e8 C-14 / U-238 nuclei, Philox draws",
-                   "substeps_per_step": sub, "parallelism": f"by-nucleus x{world}"},
-        "roofline": {"bound": "hbm", "achieved": n_mine * 20.0 * K / sec / 1e9, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": n_mine * 20.0 * K / sec / 1e9 / hbm_peak, "traffic": None,
-                     "kernel": "population_kernel", "peak_source": hbm_src,
-                     "bytes_per_nucleus_launch": 20,
-                     "note": "read zn + half-life + p (20 B); written back only for decayed nuclei"},
+                   "substeps_per_step": sub, "parallelism": f"by-nucleus x{ctx.world}",
+                   "l2_policy": "inputs larger than L2 (%.0f MB per GPU)" % (n_mine * bytes_nuc / 1e6)},
+        "roofline": {"bound": "hbm", "achieved": n_mine * bytes_nuc * K / sec / 1e9, "peak": ctx.hbm_peak,
+                     "unit": "GB/s", "frac": n_mine * bytes_nuc * K / sec / 1e9 / ctx.hbm_peak,
+                     "traffic": ncu_traffic("population_kernel") if ctx.world == 1 and sub == 1 else None,
+                     "kernel": "population_kernel", "peak_source": ctx.hbm_src,
+                     "bytes_per_nucleus_launch": bytes_nuc,
+                     "algorithmic_bytes_per_launch": n_mine * bytes_nuc, "note": note},
+        "clocks": clocks, "gpu_launches": K,
     }
+    del pop
+    torch.cuda.empty_cache()
+    return res
 
 
 if __name__ == "__main__":

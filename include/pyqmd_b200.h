@@ -75,12 +75,29 @@ int pyqmd_update_forces_and_positions(float *particles, const int32_t *types, in
  * for callers that keep float64 state (Particle.x/.y/.vx/.vy are Python floats,
  * particles.py:24-29): centre of mass (:242-243) is taken in float64, positions are made
  * nucleus-relative before the FP32 device step and restored afterwards, `n_steps` sub-steps
- * run back to back on the device (nuclear_sim.py:161-173 without decay).
+ * run back to back on the device (nuclear_sim.py:161-173 without decay).  n <= 1024 runs as one
+ * thread block (ensemble kernel); larger systems take the sorted symmetric scheme of
+ * pyqmd_cloud_step_host.  Blocking.
  */
 int pyqmd_update_particles_f64(double *x, double *y, double *vx, double *vy,
                                const uint8_t *is_proton, int64_t n, double strong_strength,
                                double coulomb_strength, double pauli_strength, double dt,
                                int32_t n_steps);
+
+/*
+ * The reference's per-step call (nuclear_forces.py:185-234: pack -> upload -> kernel -> wait ->
+ * download -> write back) for ONE system of any size whose state lives in host arrays:
+ *   h_pos, h_vel  float2[n] (in/out; pinned memory copies fastest, pageable works)
+ *   h_is_proton   uint8[n]
+ *   h_force       optional float2[n] (may be NULL): force of the last step, containment included
+ * Uploads, sorts once on the device (type bit + Morton code, stable radix sort), runs n_steps
+ * Jacobi steps of the symmetric scheme (every unordered pair once, as pyqmd_cloud_pair_forces +
+ * pyqmd_cloud_integrate below), un-sorts and downloads.  The caller's nucleon order is kept.
+ * Positions should be relative to a nearby origin (FP32).  Blocking.
+ */
+int pyqmd_cloud_step_host(float *h_pos, float *h_vel, const uint8_t *h_is_proton, float *h_force,
+                          int64_t n, float strong, float coulomb, float pauli, float dt,
+                          int32_t n_steps);
 
 /* ---------------------------------------------------------------------------------------- */
 /* (B) one large nucleon cloud resident on the device (BASELINE config 4)                    */
@@ -142,8 +159,10 @@ int pyqmd_cloud_exchange_integrate(const float *pos_in, float *vel, float *force
                                    float *const *pos_out_peers, int32_t n_peers, void *workspace,
                                    void *stream);
 
-/* 64-bit sort keys: bit 63 = neutron, low bits = 2-D Morton code of the position inside
- * [xmin, xmin+extent) x [ymin, ymin+extent).  Sorting by key gives the layout above. */
+/* 64-bit sort keys: bit 62 = neutron (protons sort first, signed or unsigned), low 48 bits = 2-D
+ * Morton code of the position inside [xmin, xmin+extent) x [ymin, ymin+extent).  A STABLE sort by
+ * key gives the layout above (stability matters when several ranks sort their replicas
+ * independently: equal keys must end up in the same order everywhere). */
 int pyqmd_cloud_sort_keys(const float *pos, const uint8_t *is_proton, int64_t n, float xmin,
                           float ymin, float extent, uint64_t *keys, void *stream);
 
@@ -296,6 +315,12 @@ int pyqmd_ensemble_census(const pyqmd_ensemble *e, unsigned long long *counts, v
 /* (D) decay-only population of particle-less nuclei (decay_chains.py:390-421; config 5)     */
 
 #define PYQMD_COUNT_COLS 16   /* per step: decays by mode [0..7], decays of watch_zn[k] [8..15] */
+/* half_life / p_decay hold caller-chosen per-nucleus values and must be read for every nucleus.  When
+ * clear (the default), they are read only for nuclides whose half-life is an ESTIMATE drawn per nucleus
+ * (PYQMD_HL_BAND); for tabulated nuclides the table row is used instead (4 B instead of 20 B of HBM
+ * traffic per nucleus and launch).  Both arrays must always be allocated and initialised: nuclei that
+ * decay write their new values back. */
+#define PYQMD_POP_PER_NUCLEUS_STATE 1
 
 typedef struct {
     int32_t *zn;
@@ -313,6 +338,8 @@ typedef struct {
     int32_t watch_zn[8];
     unsigned long long *step_counts;   /* [n_steps][PYQMD_COUNT_COLS], accumulated into */
     uint8_t *decided;         /* optional [n_steps][n]: 1 where should_decay fired */
+    int32_t flags;            /* PYQMD_POP_* */
+    int32_t reserved;
 } pyqmd_population;
 
 int pyqmd_population_step(const pyqmd_population *p, int32_t n_steps, void *stream);

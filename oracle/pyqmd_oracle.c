@@ -399,16 +399,20 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Uniform for (seed, nucleus id, step, slot) exactly as the CUDA kernels define it:
- * counter = (id_lo, id_hi, step, slot >> 1), key = (seed_lo, seed_hi); slot parity picks
- * words (0,1) or (2,3). */
+/* Uniform for (seed, nucleus id, step, slot) exactly as the CUDA kernels define it
+ * (csrc/decay_device.cuh, DrawSource), key = (seed_lo, seed_hi):
+ *   slot 0     counter (id >> 1, step, 0), words (0,1) for even ids, (2,3) for odd ids
+ *   slots 1,2  counter (id, step, 1), words (0,1) / (2,3)
+ *   slot 3     counter (id, step, 2), words (0,1) */
 double orc_philox_uniform(uint64_t seed, uint64_t id, uint32_t step, uint32_t slot)
 {
-    uint32_t ctr[4] = {(uint32_t)id, (uint32_t)(id >> 32), step, slot >> 1};
+    uint64_t c = (slot == 0) ? (id >> 1) : id;
+    uint32_t ctr[4] = {(uint32_t)c, (uint32_t)(c >> 32), step, slot == 0 ? 0u : (slot == 3 ? 2u : 1u)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];
+    int hi = (slot == 0) ? (int)(id & 1) : (slot == 2);
     orc_philox4x32_10(ctr, key, w);
-    return (slot & 1) ? orc_u53(w[2], w[3]) : orc_u53(w[0], w[1]);
+    return hi ? orc_u53(w[2], w[3]) : orc_u53(w[0], w[1]);
 }
 
 void orc_philox_uniforms(uint64_t seed, uint64_t id0, int64_t n, uint32_t step, uint32_t slot,

@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  Used by ``tests/golden/gen_golden.py`` (run in the build
 container, where /root/reference exists) to produce golden vectors, and by the
 "-m 'not gpu'" tests *when the reference happens to be present* to re-pin the oracle
-live.  Nothing on the product path and nothing that runs on the GPU box imports this.
+live; on the GPU box (where only baseline/_ref exists) by tests/test_gpu_reference_app.py and by the
+reference arm / cpu_baseline leg of bench.py.  Nothing on the product path imports this.
 
 The reference's ``nuclear_forces.py`` imports ``pyopencl`` at module top
 (nuclear_forces.py:2-3) and ``nuclear_sim.py`` imports ``pygame`` and shells out to pip for
@@ -20,10 +21,15 @@ import os
 import sys
 import types
 
-_SEARCH = [os.environ.get("PYQMD_REF", ""), "/root/reference"]
+# baseline/_ref: the unmodified reference installed by baseline/install_reference.py (git-ignored, it
+# travels to the GPU box with the snapshot); /root/reference exists in the build container only.
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SEARCH = [os.environ.get("PYQMD_REF", ""), os.path.join(_ROOT, "baseline", "_ref"), "/root/reference"]
 
 
 def reference_dir():
+    if os.environ.get("PYQMD_NO_REF"):          # tests: behave as if no reference were installed
+        return None
     for d in _SEARCH:
         if d and os.path.isfile(os.path.join(d, "nuclear_forces.py")):
             return d
@@ -51,6 +57,11 @@ class Ref:
         self.particles = importlib.import_module("particles")
         self.decay_chains = importlib.import_module("decay_chains")
         self.nuclear_forces = importlib.import_module("nuclear_forces")
+        self.dir = d
+
+    def nuclear_sim(self):
+        """The reference's application module (imports rendering -> the pygame stub)."""
+        return importlib.import_module("nuclear_sim")
 
     def forces(self, strong=150.0, coulomb=30.0, pauli=35.0):
         nf = object.__new__(self.nuclear_forces.NuclearForces)

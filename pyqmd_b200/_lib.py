@@ -22,7 +22,7 @@ HL_INF, HL_TABLE, HL_BAND = 0, 1, 2
 EXPORTS = (
     "pyqmd_abi_version", "pyqmd_last_error", "pyqmd_device_props", "pyqmd_struct_sizes",
     "pyqmd_fp32_peak",
-    "pyqmd_update_forces_and_positions", "pyqmd_update_particles_f64",
+    "pyqmd_update_forces_and_positions", "pyqmd_update_particles_f64", "pyqmd_cloud_step_host",
     "pyqmd_cloud_workspace_bytes", "pyqmd_cloud_step", "pyqmd_cloud_sort_keys",
     "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_integrate",
     "pyqmd_cloud_exchange_integrate",
@@ -85,7 +85,11 @@ class PopulationDesc(C.Structure):
         ("dt_decay", C.c_double), ("uniforms", C.c_void_p), ("uniforms_n", C.c_int64),
         ("seed", C.c_uint64), ("step0", C.c_uint32), ("n_watch", C.c_int32),
         ("watch_zn", C.c_int32 * 8), ("step_counts", C.c_void_p), ("decided", C.c_void_p),
+        ("flags", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+POP_PER_NUCLEUS_STATE = 1
 
 
 _lib = None
@@ -109,6 +113,7 @@ def lib():
     L.pyqmd_fp32_peak.argtypes = [C.c_int, C.POINTER(f64), C.POINTER(f64), vp]
     L.pyqmd_update_forces_and_positions.argtypes = [vp, vp, i32, f32, f32, f32, f32, f32, f32]
     L.pyqmd_update_particles_f64.argtypes = [vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, i32]
+    L.pyqmd_cloud_step_host.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32]
     L.pyqmd_cloud_workspace_bytes.argtypes = [i64]
     L.pyqmd_cloud_workspace_bytes.restype = i64
     L.pyqmd_cloud_step.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, f32, vp, vp]

@@ -93,6 +93,10 @@ static HostPathScratch g_scratch;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cloud_host.cu: sort once -> n_steps of the symmetric scheme -> un-sort, host arrays in and out
+int cloud_host_steps(float* h_pos, float* h_vel, const uint8_t* h_is_proton, float* h_force, int64_t n,
+                     float strong, float coulomb, float pauli, float dt, int32_t n_steps);
+
 // Runs n_steps Jacobi steps on nucleus-relative FP32 state staged in pinned memory.
 // h_pos/h_vel: float2[n] in pinned memory (in/out); h_isp: uint8[n]; centre (optional):
 // float[2] used for every step instead of the mean position.
@@ -103,13 +107,11 @@ static int run_host_steps(HostPathScratch& S, int64_t n, float strong, float cou
     const size_t b_isp = align_up((size_t)n, 256);
     unsigned char* hp = reinterpret_cast<unsigned char*>(S.pinned);
     unsigned char* dp = reinterpret_cast<unsigned char*>(S.dev);
-    // device layout: pos | vel | isp | pos2 | misc(256) | workspace
+    // device layout: pos | vel | isp | misc(256)
     float* d_pos = reinterpret_cast<float*>(dp);
     float* d_vel = reinterpret_cast<float*>(dp + b_pos);
     uint8_t* d_isp = dp + 2 * b_pos;
-    float* d_pos2 = reinterpret_cast<float*>(dp + 2 * b_pos + b_isp);
-    unsigned char* d_misc = dp + 3 * b_pos + b_isp;
-    void* d_ws = d_misc + 256;
+    unsigned char* d_misc = dp + 2 * b_pos + b_isp;
     cudaStream_t st = S.stream;
     PYQMD_CUDA_CHECK(cudaMemcpyAsync(dp, hp, 2 * b_pos + b_isp, cudaMemcpyHostToDevice, st));
 
@@ -132,21 +134,8 @@ static int run_host_steps(HostPathScratch& S, int64_t n, float strong, float cou
         rc = pyqmd_ensemble_step(&e, n_steps, st);
         if (rc != PYQMD_OK) return rc;
     } else {
-        if (centre_override) {
-            set_error("caller-supplied centre is only supported for n <= 1024");
-            return PYQMD_ERR_INVALID;
-        }
-        float* in = d_pos;
-        float* out = d_pos2;
-        for (int s = 0; s < n_steps; ++s) {
-            rc = pyqmd_cloud_step(in, out, d_vel, nullptr, d_isp, n, 0, n, strong, coulomb, pauli,
-                                  dt, d_ws, st);
-            if (rc != PYQMD_OK) return rc;
-            float* t = in; in = out; out = t;
-        }
-        if (in != d_pos)
-            PYQMD_CUDA_CHECK(cudaMemcpyAsync(d_pos, in, sizeof(float) * 2 * n,
-                                             cudaMemcpyDeviceToDevice, st));
+        set_error("run_host_steps handles n <= 1024 only");
+        return PYQMD_ERR_INVALID;
     }
     PYQMD_CUDA_CHECK(cudaMemcpyAsync(hp, dp, 2 * b_pos, cudaMemcpyDeviceToHost, st));
     PYQMD_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -157,8 +146,8 @@ static int prepare_scratch(HostPathScratch& S, int64_t n)
 {
     const size_t b_pos = align_up(sizeof(float) * 2 * n, 256);
     const size_t b_isp = align_up((size_t)n, 256);
-    const size_t ws = (size_t)pyqmd_cloud_workspace_bytes(n);
-    return S.ensure(3 * b_pos + b_isp + 256 + ws + 256, 2 * b_pos + b_isp);
+    // n > 1024 goes through cloud_host_steps, which owns its device buffers: pinned staging only
+    return S.ensure(n <= 1024 ? 2 * b_pos + b_isp + 256 : 0, 2 * b_pos + b_isp);
 }
 
 // ---- host-buffer ensemble pipeline: three in-order lanes linked by per-chunk events ------------------
@@ -410,8 +399,12 @@ extern "C" int pyqmd_update_particles_f64(double* x, double* y, double* vx, doub
         h_vel[2 * i + 1] = (float)vy[i];
         h_isp[i] = is_proton[i] ? 1 : 0;
     }
-    rc = run_host_steps(S, n, (float)strong_strength, (float)coulomb_strength,
-                        (float)pauli_strength, (float)dt, n_steps, nullptr);
+    if (n <= 1024)
+        rc = run_host_steps(S, n, (float)strong_strength, (float)coulomb_strength,
+                            (float)pauli_strength, (float)dt, n_steps, nullptr);
+    else       // one large system: sorted symmetric scheme (cloud_host.cu)
+        rc = cloud_host_steps(h_pos, h_vel, h_isp, nullptr, n, (float)strong_strength,
+                              (float)coulomb_strength, (float)pauli_strength, (float)dt, n_steps);
     if (rc != PYQMD_OK) return rc;
     for (int64_t i = 0; i < n; ++i) {
         x[i] = (double)h_pos[2 * i] + cx;

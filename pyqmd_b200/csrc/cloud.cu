@@ -347,31 +347,14 @@ cloud_integrate_kernel(const float2* __restrict__ pos_in, float2* __restrict__ p
     if (force) force[i] = make_float2(Fx, Fy);         // containment is part of the reported force
 }
 
-// ---- sort keys -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t spread_bits(uint32_t v)
-{
-    uint64_t x = v;
-    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
-    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
-    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
-    x = (x | (x << 2)) & 0x3333333333333333ull;
-    x = (x | (x << 1)) & 0x5555555555555555ull;
-    return x;
-}
-
+// ---- sort keys (cloud_sort_key: cloud.cuh) ---------------------------------------------------------
 __global__ void cloud_sort_keys_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp,
                                        int64_t n, float xmin, float ymin, float inv_extent,
                                        uint64_t* __restrict__ keys)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float2 p = pos[i];
-    const float ux = fminf(fmaxf((p.x - xmin) * inv_extent, 0.f), 0.99999994f);
-    const float uy = fminf(fmaxf((p.y - ymin) * inv_extent, 0.f), 0.99999994f);
-    const uint32_t qx = (uint32_t)(ux * 16777216.f), qy = (uint32_t)(uy * 16777216.f);
-    uint64_t key = spread_bits(qx) | (spread_bits(qy) << 1);
-    if (!isp[i]) key |= (1ull << 63);
-    keys[i] = key;
+    keys[i] = cloud_sort_key(pos[i], isp[i] != 0, xmin, ymin, inv_extent);
 }
 
 // tile statistics + centre of mass, shared with the symmetric scheme (cloud_sym.cu)

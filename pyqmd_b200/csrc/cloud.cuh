@@ -57,6 +57,30 @@ inline CloudWorkspace carve(void* ws, int64_t n)
     return w;
 }
 
+// ---- sort keys -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread_bits(uint32_t v)
+{
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
+// 64-bit sort key: bit 62 = neutron (protons first for signed and unsigned sorts alike), low 48 bits
+// = 2-D Morton code of the position inside [xmin, xmin + extent) x [ymin, ymin + extent)
+__device__ __forceinline__ uint64_t cloud_sort_key(float2 p, bool proton, float xmin, float ymin, float inv_extent)
+{
+    const float ux = fminf(fmaxf((p.x - xmin) * inv_extent, 0.f), 0.99999994f);
+    const float uy = fminf(fmaxf((p.y - ymin) * inv_extent, 0.f), 0.99999994f);
+    const uint32_t qx = (uint32_t)(ux * 16777216.f), qy = (uint32_t)(uy * 16777216.f);
+    uint64_t key = spread_bits(qx) | (spread_bits(qy) << 1);
+    if (!proton) key |= (1ull << 62);
+    return key;
+}
+
 struct FarConsts {
     f32x2 kexp, logA, l1, l2, g1, g2, one, negC;
 };

@@ -45,13 +45,6 @@ struct SymParams {
     float scale;                      // 2^k, fixed-point scale of the accumulators
 };
 
-__device__ __forceinline__ f32x2 shfl64(f32x2 v, int src)
-{
-    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(v & 0xffffffffull), src);
-    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
-    return ((f32x2)hi << 32) | lo;
-}
-
 // Two far pairs (one i, two j), action on i and (REACT) reaction on the two j.
 template <int MODE, bool REACT>
 __device__ __forceinline__ void far_pair2_sym(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,

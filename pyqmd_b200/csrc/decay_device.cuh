@@ -43,37 +43,44 @@ __device__ __forceinline__ double u53(uint32_t w0, uint32_t w1)
 // Draw source for one nucleus-step.  Slot meaning: 0 should_decay (particles.py:147),
 // 1 branch (decay_chains.py:221), 2 emission angle (:332..367), 3 half-life estimate (:312-328).
 // With `uniforms` != nullptr the draws are read from a caller-supplied [step][nucleus][4] array
-// (the bit-exact parity path); otherwise Philox keyed by seed with counter
-// (id_lo, id_hi, step, slot >> 1) -- independent of how nuclei are sharded over GPUs.
+// (the bit-exact parity path); otherwise Philox4x32-10 keyed by seed, counters built from GLOBAL ids
+// -- independent of how nuclei are sharded over GPUs:
+//   slot 0     counter (id >> 1, step, 0): words (0,1) for even ids, (2,3) for odd ids -- ONE call
+//              serves the every-step draw of two neighbouring nuclei (the decay-only population
+//              kernel keeps two nuclei per thread for exactly this reason)
+//   slots 1,2  counter (id, step, 1): words (0,1) / (2,3)     -- only when a nucleus decays
+//   slot 3     counter (id, step, 2): words (0,1)             -- only for estimated half-lives
+// (oracle twin: orc_philox_uniform, oracle/pyqmd_oracle.c)
 struct DrawSource {
     const double* uniforms;   // optional [step_rel][uniforms_n][4]
     uint64_t seed;
     int64_t uniforms_n;       // nuclei per step in the uniforms array
 
-    // id_global / step_abs feed the Philox counter; id_local / step_rel index `uniforms`.
-    __device__ __forceinline__ void pair(uint64_t id_global, int64_t id_local, uint32_t step_abs,
-                                         uint32_t step_rel, uint32_t slot_pair, double& ua,
-                                         double& ub) const
+    // slot-0 draws of the nuclei 2 * pair_id and 2 * pair_id + 1 from one Philox call
+    __device__ __forceinline__ void slot0_pair(uint64_t pair_id, uint32_t step_abs, double& u_even,
+                                               double& u_odd) const
     {
-        if (uniforms) {
-            const double* p =
-                uniforms + ((int64_t)step_rel * uniforms_n + id_local) * 4 + slot_pair * 2;
-            ua = p[0];
-            ub = p[1];
-        } else {
-            uint32_t w[4];
-            philox4x32_10((uint32_t)id_global, (uint32_t)(id_global >> 32), step_abs, slot_pair,
-                          (uint32_t)seed, (uint32_t)(seed >> 32), w);
-            ua = u53(w[0], w[1]);
-            ub = u53(w[2], w[3]);
-        }
+        uint32_t w[4];
+        philox4x32_10((uint32_t)pair_id, (uint32_t)(pair_id >> 32), step_abs, 0u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), w);
+        u_even = u53(w[0], w[1]);
+        u_odd = u53(w[2], w[3]);
     }
+
+    // id_global / step_abs feed the Philox counter; id_local / step_rel index `uniforms`.
     __device__ __forceinline__ double one(uint64_t id_global, int64_t id_local, uint32_t step_abs,
                                           uint32_t step_rel, uint32_t slot) const
     {
-        double a, b;
-        pair(id_global, id_local, step_abs, step_rel, slot >> 1, a, b);
-        return (slot & 1) ? b : a;
+        if (uniforms) return uniforms[((int64_t)step_rel * uniforms_n + id_local) * 4 + slot];
+        if (slot == 0) {
+            double a, b;
+            slot0_pair(id_global >> 1, step_abs, a, b);
+            return (id_global & 1) ? b : a;
+        }
+        uint32_t w[4];
+        philox4x32_10((uint32_t)id_global, (uint32_t)(id_global >> 32), step_abs, slot == 3 ? 2u : 1u,
+                      (uint32_t)seed, (uint32_t)(seed >> 32), w);
+        return (slot == 2) ? u53(w[2], w[3]) : u53(w[0], w[1]);
     }
 };
 

@@ -6,13 +6,12 @@
 // the physics slice of handle_decay (nuclear_sim.py:213,288-294,349,353) and
 // NuclearForces.update_particles_cpu (nuclear_forces.py:236-323).
 //
-// Layout: a block of T threads holds G = T / cap nuclei (cap = largest nucleon count in the
-// launch's size bin); thread t owns nucleon (t % cap) of nucleus (t / cap).  Positions and
-// types live in shared memory as float4 (x, y, isProton, 0) so the j loop is one broadcast
-// LDS.128 per pair; velocities and force accumulators stay in registers.  The update is
-// Jacobi (double-buffered through registers + a barrier), like the reference CPU path and
-// unlike its racy OpenCL kernel.  HBM is touched once on entry and once on exit, whatever
-// n_steps is.
+// Layout: see ensemble_ring_kernel below -- every unordered pair once on warp-local rings, positions
+// and types in shared memory as SoA, velocities and force accumulators in registers.  The update is
+// Jacobi (double-buffered through registers + a barrier), like the reference CPU path and unlike
+// its racy OpenCL kernel.  HBM is touched once on entry and once on exit, whatever n_steps is.
+#include <mutex>
+
 #include "common.cuh"
 #include "decay_device.cuh"
 #include "pair_law.cuh"
@@ -82,9 +81,9 @@ __device__ void leader_decay(const pyqmd_ensemble& e, const DrawSource& draws, f
     // products(x, y), nuclear_sim.py:294 -> decay_chains.py:331-371
     int ptype = -1;
     double speed = 0.0, vx = 0.0, vy = 0.0;
-    double u2 = 0.0, u3 = 0.0;
-    draws.pair(gid, nuc, step_abs, step_rel, 1, u2, u3);
+    double u2 = 0.0;
     if (emission_of(mode, ptype, speed)) {
+        u2 = draws.one(gid, nuc, step_abs, step_rel, 2);
         const double ang = __dmul_rn(6.283185307179586, u2);   // uniform(0, 2*pi)
         vx = speed * cos(ang);
         vy = speed * sin(ang);
@@ -105,54 +104,158 @@ __device__ void leader_decay(const pyqmd_ensemble& e, const DrawSource& draws, f
     if (e.mode_counts) atomicAdd(e.mode_counts + mode, 1ULL);
 
     // nucleus.stability = get_half_life(Z', N'), nuclear_sim.py:353
+    const pyqmd_nuclide_entry* nxt = lookup(e.table, zn);
+    const double u3 = (nxt->kind == PYQMD_HL_BAND) ? draws.one(gid, nuc, step_abs, step_rel, 3) : 0.0;
     bool used3;
-    daughter_half_life(lookup(e.table, zn), u3, e.dt_decay, T, p, used3);
+    daughter_half_life(nxt, u3, e.dt_decay, T, p, used3);
 }
 
-// Per-warp sums of the nucleon positions of a block (G == 1: the whole block is one nucleus),
-// written next to the positions so that the centre of mass (nuclear_forces.py:242-243) needs no
-// barrier of its own; summed by every thread in warp order, i.e. deterministically.
-__device__ __forceinline__ void publish_warp_sum(float2* wsum, float x, float y, bool active)
+// ---------------------------------------------------------------------------------------------------
+// ensemble_ring_kernel: the production kernel for nuclei of up to 1024 nucleons.
+//
+// Every unordered pair of a nucleus is evaluated ONCE (F_ij = -F_ji holds exactly for this law: it
+// depends on d and on symmetric type predicates only) by warp-local rings:
+//
+//   * a lane owns kQ = 4 consecutive nucleons (a "subgroup"), a warp a group of Pe <= 32 subgroups,
+//     a nucleus nG = 1..8 groups (one warp each); nuclei of <= 64 nucleons share a warp (K per warp).
+//   * diagonal block (group x itself): at ring step m lane l meets subgroup (l + m) mod Pe of its own
+//     group, m = 1 .. (Pe-1)/2 (+ the antipode for the lower half when Pe is even), 16 pairs per lane
+//     and step, all packed f32x2 (two j per instruction); the pairs inside a subgroup are done once
+//     more in ordered form (m = 0, no reaction).
+//   * off-diagonal blocks: group w meets the groups w+1 .. w+(nG-1)/2 (mod nG) in full (Pe steps) and,
+//     for even nG, half of the steps against group w + nG/2 (the partner does the other half).
+//   * the REACTION accumulators of a j subgroup travel with it from lane to lane (SHFL), exactly as in
+//     cloud_sym_kernel: no shared-memory read-modify-write, no atomics, fixed summation order =>
+//     bit-reproducible.  After a diagonal ring they are shuffled home; after an off-diagonal block
+//     they are written once to the per-distance reaction row of the target group.
+//
+// Shared memory per nucleus (slots = nG * P * 4): X, Y, T float[slots] (SoA: one LDS.128 fetches the
+// 4 x / y / types of a subgroup, conflict-free because lanes read consecutive 16-byte words),
+// react float2[nG/2][slots], and a canonical staging area (float4 + float2 per slot) that is touched
+// only when a nucleus decays.  Padding slots hold ghost neutrons parked at (1e5, 1e5): every term of
+// the law is exactly 0 at that distance (and two ghosts coincide: skipped), so no masking is needed.
+constexpr float kGhost = 1.0e5f;
+constexpr int kQ = 4;
+
+struct RingGeom {
+    int nG;      // warps (groups) per nucleus
+    int P;       // lanes per group at full capacity (cap nucleons)
+    int K;       // nuclei per warp (nG == 1 only)
+    int slots;   // shared-memory slots per nucleus = nG * P * kQ
+    int warps;   // warps per block
+    int G;       // nuclei per block
+};
+
+static RingGeom ring_geom(int cap)
 {
-    float sx = active ? x : 0.f, sy = active ? y : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    RingGeom g;
+    int S = (cap + kQ - 1) / kQ;
+    if (S < 1) S = 1;
+    if (S <= 32) {
+        g.nG = 1; g.P = S; g.K = 32 / S; g.warps = 4;
+    } else {
+        g.nG = (S + 31) / 32; g.P = (S + g.nG - 1) / g.nG; g.K = 1; g.warps = g.nG;
     }
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = make_float2(sx, sy);
+    g.slots = g.nG * g.P * kQ;
+    g.G = (g.nG == 1) ? g.warps * g.K : 1;
+    return g;
 }
 
-// N3 = true: every unordered pair is evaluated once (F_ij = -F_ji holds exactly for this law:
-// it depends on d and on symmetric type predicates only) on a ring schedule -- nucleon i visits
-// partners i+1 .. i+(n-1)/2 (mod n), plus i+n/2 for the lower half when n is even -- and the
-// reaction is accumulated in a per-warp shared-memory row (no atomics, fixed order, so results
-// are reproducible).  Halves the MUFU and FMA work per ordered pair.  N3 = false is the plain
-// ordered-pair loop, kept for blocks of more than 256 threads where the per-warp reaction rows
-// would not fit in shared memory.
-template <int MAXT, bool N3>
-__global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, const LawParams L,
-                                                         const int n_steps, const int G)
+static size_t ring_smem_bytes(const RingGeom& g)
+{
+    const size_t nSl = (size_t)g.G * g.slots;
+    return nSl * (3 * sizeof(float) + (size_t)(g.nG / 2) * sizeof(float2) + sizeof(float4) +
+                  sizeof(float2)) + (size_t)g.warps * sizeof(float2) + (size_t)g.G * sizeof(int) + 16;
+}
+
+struct Reacts {
+    f32x2 x01, y01, x23, y23;     // sum of dx * s (resp. dy * s) over the i side, per j of the subgroup
+};
+
+__device__ __forceinline__ void rotate(Reacts& r, int src)
+{
+    r.x01 = shfl64(r.x01, src); r.y01 = shfl64(r.y01, src);
+    r.x23 = shfl64(r.x23, src); r.y23 = shfl64(r.y23, src);
+}
+
+// The 4 i-nucleons of a lane against the 4 j-nucleons of one subgroup: 16 pairs, 8 packed evaluations
+// of the general law (nuclear_forces.py:253-298).
+template <bool REACT>
+__device__ __forceinline__ void ring_visit(const ulonglong2 X, const ulonglong2 Y, const float4 T,
+                                           const f32x2 (&xi2)[kQ], const f32x2 (&yi2)[kQ],
+                                           const float (&ti)[kQ], f32x2 (&ax)[kQ], f32x2 (&ay)[kQ],
+                                           Reacts& r, const GenConsts& gc, const LawParams& L,
+                                           const f32x2 negC)
+{
+    const f32x2 nq01 = mul2(negC, pk(T.x, T.y)), nq23 = mul2(negC, pk(T.z, T.w));
+#pragma unroll
+    for (int k = 0; k < kQ; ++k) {
+        const f32x2 ti2 = pk1(ti[k]);
+        {
+            const f32x2 dx = sub2(X.x, xi2[k]), dy = sub2(Y.x, yi2[k]);
+            const f32x2 s = pair_general2(dx, dy, T.x, T.y, ti[k], ti2, nq01, gc, L);
+            ax[k] = fma2(dx, s, ax[k]);
+            ay[k] = fma2(dy, s, ay[k]);
+            if (REACT) { r.x01 = fma2(dx, s, r.x01); r.y01 = fma2(dy, s, r.y01); }
+        }
+        {
+            const f32x2 dx = sub2(X.y, xi2[k]), dy = sub2(Y.y, yi2[k]);
+            const f32x2 s = pair_general2(dx, dy, T.z, T.w, ti[k], ti2, nq23, gc, L);
+            ax[k] = fma2(dx, s, ax[k]);
+            ay[k] = fma2(dy, s, ay[k]);
+            if (REACT) { r.x23 = fma2(dx, s, r.x23); r.y23 = fma2(dy, s, r.y23); }
+        }
+    }
+}
+
+#ifndef PYQMD_RING_MINBLOCKS_SINGLE
+#define PYQMD_RING_MINBLOCKS_SINGLE 4
+#endif
+#ifndef PYQMD_RING_MINBLOCKS_PAIR
+#define PYQMD_RING_MINBLOCKS_PAIR 8
+#endif
+
+// MULTI = true: one nucleus per block of nG >= 2 warps (MAXT = 64: the two-warp case, 129..256
+// nucleons, tuned on Pb-208 / U-238; MAXT = 256: up to 8 warps); MULTI = false: every warp is on its
+// own (K >= 1 nuclei per warp, MAXT = 128), so only warp-level synchronisation is used.
+template <bool MULTI, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+ensemble_ring_kernel(const pyqmd_ensemble e, const LawParams L, const int n_steps, const RingGeom geo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x;
-    const int nW = T >> 5;
-    float4* sp = reinterpret_cast<float4*>(smem_raw);
-    float2* sv = reinterpret_cast<float2*>(sp + T);
-    float2* react = sv + T;                                  // [nW][T], N3 only
-    float2* wsum = react + (N3 ? nW * T : 0);                // [nW]
-    int* scnt = reinterpret_cast<int*>(wsum + nW);
+    const int nSl = geo.G * geo.slots;
+    const int nR = geo.nG >> 1;
+    float* sX = reinterpret_cast<float*>(smem_raw);
+    float* sY = sX + nSl;
+    float* sT = sY + nSl;
+    float2* sReact = reinterpret_cast<float2*>(sT + nSl);          // [nR][nSl]
+    float4* spc = reinterpret_cast<float4*>(sReact + (size_t)nR * nSl);
+    float2* sv = reinterpret_cast<float2*>(spc + nSl);
+    float2* wsum = sv + nSl;                                        // [warps]
+    int* scnt = reinterpret_cast<int*>(wsum + geo.warps);           // [G]
 
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int cap = e.cap;
-    const int g = tid / cap;
-    const int li = tid - g * cap;
-    const int gbase = g * cap;
-    const int64_t q = (int64_t)blockIdx.x * G + g;
-    const bool has_nuc = (g < G) && (q < e.n_list);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // MULTI or K == 1: the whole warp serves one nucleus (lanes >= Pe idle along: every lane must see
+    // the same count, the ring trip counts have to be warp-uniform); K > 1: `sub` picks the team.
+    int sub = 0, l = lane, grp = warp, g = 0;
+    if (!MULTI) {
+        grp = 0;
+        if (geo.K > 1) {
+            sub = lane / geo.P;
+            l = lane - sub * geo.P;
+        }
+        g = warp * geo.K + sub;
+    }
+    const bool in_team = sub < geo.K;
+    if (!in_team) g = warp * geo.K;                                 // keep shared-memory indices in range
+    const int tbase = MULTI ? 0 : sub * geo.P;                      // first lane of the team
+    const int64_t q = (int64_t)blockIdx.x * geo.G + g;
+    const bool has_nuc = in_team && q < e.n_list;
+    if (!MULTI && !__any_sync(0xffffffffu, has_nuc)) return;        // this warp has nothing to do
     const int nuc = has_nuc ? (e.list ? e.list[q] : (int)q) : -1;
-    const bool leader = has_nuc && li == 0;
+    const bool leader = has_nuc && l == 0 && grp == 0;
+    const int gb = g * geo.slots;                                   // first slot of the nucleus
+    const bool per_count_ring = MULTI || geo.K == 1;                // ring length follows the live count
 
     int cnt = 0;
     int64_t off = 0;
@@ -160,24 +263,68 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
         cnt = e.count[nuc];
         off = e.offset[nuc];
     }
-    float x = 0.f, y = 0.f, tp = 0.f;
-    float2 vel = make_float2(0.f, 0.f);
-    if (has_nuc && li < cnt) {
-        const float2 p2 = reinterpret_cast<const float2*>(e.pos)[off + li];
-        vel = reinterpret_cast<const float2*>(e.vel)[off + li];
-        x = p2.x; y = p2.y;
-        tp = e.is_proton[off + li] ? 1.0f : 0.0f;
-    }
-    sp[tid] = make_float4(x, y, tp, 0.f);
-    if (li == 0 && g < G) scnt[g] = cnt;
-    if (N3)
-        for (int w = 0; w < nW; ++w) react[w * T + tid] = make_float2(0.f, 0.f);
-    publish_warp_sum(wsum, x, y, has_nuc && li < cnt);
-    // warps that can hold nucleons of this thread's nucleus
-    const int w_lo = gbase >> 5;
-    const int w_hi = min((gbase + cap - 1) >> 5, nW - 1);
+    auto ring_len = [&](int c) {
+        if (!per_count_ring) return geo.P;                          // trip counts must be warp-uniform
+        int S = (c + kQ - 1) / kQ;
+        if (S < 1) S = 1;
+        return MULTI ? (S + geo.nG - 1) / geo.nG : S;
+    };
+    int Pe = ring_len(cnt);
+    bool active = in_team && l < Pe;
+    int s0 = (grp * Pe + (active ? l : 0)) * kQ;                    // first slot of this lane
 
-    // leader-held nucleus state
+    float xi[kQ], yi[kQ], ti[kQ];
+    float2 vi[kQ];
+    auto load_global = [&]() {
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) {
+            xi[k] = kGhost; yi[k] = kGhost; ti[k] = 0.f;
+            vi[k] = make_float2(0.f, 0.f);
+            if (active && s0 + k < cnt) {
+                const float2 p = reinterpret_cast<const float2*>(e.pos)[off + s0 + k];
+                vi[k] = reinterpret_cast<const float2*>(e.vel)[off + s0 + k];
+                xi[k] = p.x; yi[k] = p.y;
+                ti[k] = e.is_proton[off + s0 + k] ? 1.0f : 0.0f;
+            }
+        }
+    };
+    // own subgroup -> shared memory, and the nucleus' coordinate sums (nuclear_forces.py:242-243)
+    float sumx = 0.f, sumy = 0.f;
+    auto publish = [&]() {
+        if (active) {
+            reinterpret_cast<float4*>(sX + gb)[s0 >> 2] = make_float4(xi[0], xi[1], xi[2], xi[3]);
+            reinterpret_cast<float4*>(sY + gb)[s0 >> 2] = make_float4(yi[0], yi[1], yi[2], yi[3]);
+            reinterpret_cast<float4*>(sT + gb)[s0 >> 2] = make_float4(ti[0], ti[1], ti[2], ti[3]);
+        }
+        float px = 0.f, py = 0.f;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k)
+            if (active && s0 + k < cnt) { px += xi[k]; py += yi[k]; }
+        if (MULTI || geo.K == 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                px += __shfl_xor_sync(0xffffffffu, px, o);
+                py += __shfl_xor_sync(0xffffffffu, py, o);
+            }
+            if (MULTI && lane == 0) wsum[warp] = make_float2(px, py);
+            sumx = px; sumy = py;
+        } else {
+            float ax_ = 0.f, ay_ = 0.f;
+            for (int j = 0; j < geo.P; ++j) {                       // fixed order, team by team
+                ax_ += __shfl_sync(0xffffffffu, px, min(tbase + j, 31));
+                ay_ += __shfl_sync(0xffffffffu, py, min(tbase + j, 31));
+            }
+            sumx = ax_; sumy = ay_;
+        }
+    };
+    auto team_sync = [&]() {
+        if (MULTI) __syncthreads(); else __syncwarp();
+    };
+
+    load_global();
+    if (leader) scnt[g] = cnt;
+    publish();
+
     int32_t zn = 0;
     double T_half = 0.0, p_dec = -1.0;
     if (leader && e.decay_enabled) {
@@ -185,8 +332,11 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
         T_half = e.half_life[nuc];
         p_dec = e.p_decay[nuc];
     }
-    DrawSource draws{e.uniforms, e.seed, e.uniforms_n};
+    const DrawSource draws{e.uniforms, e.seed, e.uniforms_n};
+    const GenConsts gc = make_gen_consts(L);
+    const f32x2 negC = pk1(-L.C);
     float R = 2.4f * cbrtf((float)cnt);                     // nuclear_forces.py:304
+    team_sync();
 
     for (int s = 0; s < n_steps; ++s) {
         // ---- decay test: Nucleus.should_decay, particles.py:126-147 --------------------------
@@ -197,112 +347,178 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
                 const double u0 = draws.one((uint64_t)(e.id_base + nuc), nuc, step_abs, s, 0);
                 fire = u0 < p_dec;                          // :147
             }
-            if (__syncthreads_or(fire)) {
-                sv[tid] = vel;
-                __syncthreads();
+            const bool any_fire = MULTI ? (__syncthreads_or(fire) != 0)
+                                        : (__any_sync(0xffffffffu, fire) != 0);
+            if (any_fire) {
+                // canonical (list-order) staging: slot index == position in Nucleus.particles
+#pragma unroll
+                for (int k = 0; k < kQ; ++k)
+                    if (active && s0 + k < cnt) {
+                        spc[gb + s0 + k] = make_float4(xi[k], yi[k], ti[k], 0.f);
+                        sv[gb + s0 + k] = vi[k];
+                    }
+                team_sync();
                 if (fire) {
-                    leader_decay(e, draws, sp, sv, gbase, cnt, nuc, step_abs, s, zn, T_half, p_dec);
+                    leader_decay(e, draws, spc, sv, gb, cnt, nuc, step_abs, s, zn, T_half, p_dec);
                     scnt[g] = cnt;
                 }
-                __syncthreads();
-                if (g < G) cnt = scnt[g];
-                vel = sv[tid];
-                const float4 me = sp[tid];
-                x = me.x; y = me.y; tp = me.z;
+                team_sync();
+                if (has_nuc) cnt = scnt[g];
+                Pe = ring_len(cnt);
+                active = in_team && l < Pe;
+                s0 = (grp * Pe + (active ? l : 0)) * kQ;
+#pragma unroll
+                for (int k = 0; k < kQ; ++k) {
+                    xi[k] = kGhost; yi[k] = kGhost; ti[k] = 0.f;
+                    vi[k] = make_float2(0.f, 0.f);
+                    if (active && s0 + k < cnt) {
+                        const float4 a = spc[gb + s0 + k];
+                        xi[k] = a.x; yi[k] = a.y; ti[k] = a.z;
+                        vi[k] = sv[gb + s0 + k];
+                    }
+                }
                 R = 2.4f * cbrtf((float)cnt);
-                publish_warp_sum(wsum, x, y, has_nuc && li < cnt);
-                __syncthreads();
+                team_sync();                                // staging consumed before X / Y / T move
+                publish();
+                team_sync();
             }
-        } else {
-            __syncthreads();
         }
 
-        const bool active = has_nuc && li < cnt;
-        float fx = 0.f, fy = 0.f;
+        // ---- centre of mass, nuclear_forces.py:242-243 --------------------------------------------
         float cx = 0.f, cy = 0.f;
-        if (active) {
-            // ---- centre of mass, nuclear_forces.py:242-243 ----------------------------------------
-            const float4* tile = sp + gbase;
+        if (has_nuc) {
             if (e.centre) {                                 // caller-supplied `center`, :64
                 cx = e.centre[2 * (int64_t)nuc];
                 cy = e.centre[2 * (int64_t)nuc + 1];
             } else {
-                float sx = 0.f, sy = 0.f;
-                if (G == 1) {
-                    for (int w = 0; w < nW; ++w) { sx += wsum[w].x; sy += wsum[w].y; }
-                } else {
-                    for (int j = 0; j < cnt; ++j) { sx += tile[j].x; sy += tile[j].y; }
+                float sx = sumx, sy = sumy;
+                if (MULTI) {
+                    sx = 0.f; sy = 0.f;
+                    for (int w = 0; w < geo.nG; ++w) { sx += wsum[w].x; sy += wsum[w].y; }
                 }
-                const float inv_n = 1.0f / (float)cnt;
+                const float inv_n = 1.0f / (float)max(cnt, 1);
                 cx = sx * inv_n;
                 cy = sy * inv_n;
             }
-            // ---- all-pairs force, nuclear_forces.py:248-298 ---------------------------------------
-            if (N3) {
-                float2* row = react + warp * T + gbase;
-                const int half = (cnt - 1) >> 1;
-                int j = li;
-#pragma unroll 2
-                for (int k = 0; k < half; ++k) {
-                    j = (j + 1 == cnt) ? 0 : j + 1;         // partner (li + k + 1) mod cnt
-                    const float4 o = tile[j];
-                    const float dx = o.x - x, dy = o.y - y;
-                    const float sc = pair_general(dx, dy, tp, o.z, L);
-                    const float px = dx * sc, py = dy * sc;
-                    fx += px;
-                    fy += py;
-                    float2 r = row[j];                      // reaction on the partner
-                    r.x -= px;
-                    r.y -= py;
-                    row[j] = r;
+        }
+
+        // ---- all-pairs force, nuclear_forces.py:248-298 ---------------------------------------------
+        f32x2 ax[kQ], ay[kQ], xi2[kQ], yi2[kQ];
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) {
+            ax[k] = 0ull; ay[k] = 0ull;
+            xi2[k] = pk1(xi[k]);
+            yi2[k] = pk1(yi[k]);
+        }
+        const int lq = active ? l : 0;
+        const int src = active ? ((l + 1 == Pe) ? tbase : lane + 1) : lane;   // the ring neighbour
+        const ulonglong2* X4 = reinterpret_cast<const ulonglong2*>(sX + gb);
+        const ulonglong2* Y4 = reinterpret_cast<const ulonglong2*>(sY + gb);
+        const float4* T4 = reinterpret_cast<const float4*>(sT + gb);
+        Reacts rd = {0ull, 0ull, 0ull, 0ull};
+        {
+            // pairs inside the subgroup: ordered, no reaction (the self pairs are skipped by d2 < 0.01)
+            Reacts none = {0ull, 0ull, 0ull, 0ull};
+            ring_visit<false>(make_ulonglong2(pk(xi[0], xi[1]), pk(xi[2], xi[3])),
+                              make_ulonglong2(pk(yi[0], yi[1]), pk(yi[2], yi[3])),
+                              make_float4(ti[0], ti[1], ti[2], ti[3]), xi2, yi2, ti, ax, ay, none, gc, L,
+                              negC);
+            // diagonal ring of the lane's own group
+            const int own = grp * Pe;
+            const int hs = (Pe - 1) >> 1;
+            int qd = lq;
+#pragma unroll 1
+            for (int m = 1; m <= hs; ++m) {
+                qd = (qd + 1 == Pe) ? 0 : qd + 1;
+                ring_visit<true>(X4[own + qd], Y4[own + qd], T4[own + qd], xi2, yi2, ti, ax, ay, rd, gc,
+                                 L, negC);
+                rotate(rd, src);
+            }
+            if (!(Pe & 1)) {                                // antipodal subgroup, lower half only
+                if (active && l < (Pe >> 1)) {
+                    const int qa = own + l + (Pe >> 1);
+                    ring_visit<true>(X4[qa], Y4[qa], T4[qa], xi2, yi2, ti, ax, ay, rd, gc, L, negC);
                 }
-                if (!(cnt & 1) && li < (cnt >> 1)) {        // antipodal partner, even n
-                    j = li + (cnt >> 1);
-                    const float4 o = tile[j];
-                    const float dx = o.x - x, dy = o.y - y;
-                    const float sc = pair_general(dx, dy, tp, o.z, L);
-                    const float px = dx * sc, py = dy * sc;
-                    fx += px;
-                    fy += py;
-                    float2 r = row[j];
-                    r.x -= px;
-                    r.y -= py;
-                    row[j] = r;
+                rotate(rd, src);
+            }
+            // lane l now holds the reaction of subgroup (l + Pe/2 + 1) mod Pe: bring it home
+            int from = lq - (Pe >> 1) - 1;
+            from += (from < 0) ? Pe : 0;
+            from += (from < 0) ? Pe : 0;
+            rotate(rd, active ? tbase + from : lane);
+        }
+        if (MULTI) {
+            // off-diagonal blocks: groups grp+1 .. grp+nG/2 (the last one shared with the partner)
+            for (int dlt = 1; dlt <= nR; ++dlt) {
+                int tg = grp + dlt;
+                tg -= (tg >= geo.nG) ? geo.nG : 0;
+                int m0 = 0, m1 = Pe;
+                if (2 * dlt == geo.nG) {
+                    const int h = (Pe + 1) >> 1;
+                    if (grp < nR) { m0 = 0; m1 = h; } else { m0 = 1; m1 = Pe - h + 1; }
                 }
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 o = tile[j];
-                    const float dx = o.x - x, dy = o.y - y;
-                    const float sc = pair_general(dx, dy, tp, o.z, L);
-                    fx = fmaf(dx, sc, fx);
-                    fy = fmaf(dy, sc, fy);
+                Reacts ro = {0ull, 0ull, 0ull, 0ull};
+                const int base = tg * Pe;
+                int qo = lq + m0;
+                qo -= (qo >= Pe) ? Pe : 0;
+#pragma unroll 1
+                for (int m = m0; m < m1; ++m) {
+                    ring_visit<true>(X4[base + qo], Y4[base + qo], T4[base + qo], xi2, yi2, ti, ax, ay, ro,
+                                     gc, L, negC);
+                    rotate(ro, src);
+                    qo = (qo + 1 == Pe) ? 0 : qo + 1;
+                }
+                if (active) {                               // lane l holds subgroup (l + m1) mod Pe of tg
+                    float a, b, c2, d;
+                    float4* row = reinterpret_cast<float4*>(sReact + (size_t)(dlt - 1) * nSl + gb) +
+                                  2 * (base + qo);
+                    upk(ro.x01, a, b);
+                    upk(ro.y01, c2, d);
+                    row[0] = make_float4(a, c2, b, d);
+                    upk(ro.x23, a, b);
+                    upk(ro.y23, c2, d);
+                    row[1] = make_float4(a, c2, b, d);
                 }
             }
         }
-        __syncthreads();                 // Jacobi: all reads (and all reactions) before any write
-        if (active) {
-            if (N3) {
-                for (int w = w_lo; w <= w_hi; ++w) {        // fixed order: reproducible
-                    const float2 r = react[w * T + tid];
-                    react[w * T + tid] = make_float2(0.f, 0.f);
-                    fx += r.x;
-                    fy += r.y;
+        team_sync();                 // Jacobi: all reads (and all reactions) before any write
+        {
+            float rx[kQ], ry[kQ];
+            upk(rd.x01, rx[0], rx[1]); upk(rd.x23, rx[2], rx[3]);
+            upk(rd.y01, ry[0], ry[1]); upk(rd.y23, ry[2], ry[3]);
+#pragma unroll
+            for (int k = 0; k < kQ; ++k) {
+                float a, b;
+                upk(ax[k], a, b);
+                float fx = (a + b) - rx[k];
+                upk(ay[k], a, b);
+                float fy = (a + b) - ry[k];
+                if (MULTI && active) {
+                    for (int dlt = 1; dlt <= nR; ++dlt) {   // fixed order: reproducible
+                        const float2 rr = sReact[(size_t)(dlt - 1) * nSl + gb + s0 + k];
+                        fx -= rr.x;
+                        fy -= rr.y;
+                    }
+                }
+                if (active && s0 + k < cnt) {
+                    contain_and_integrate(xi[k], yi[k], vi[k].x, vi[k].y, fx, fy, cx, cy, R,
+                                          e.dt_phys);                                // :301-323
+                    if (e.force && s == n_steps - 1)
+                        reinterpret_cast<float2*>(e.force)[off + s0 + k] = make_float2(fx, fy);
                 }
             }
-            contain_and_integrate(x, y, vel.x, vel.y, fx, fy, cx, cy, R, e.dt_phys);   // :301-323
-            sp[tid] = make_float4(x, y, tp, 0.f);
-            if (e.force && s == n_steps - 1)
-                reinterpret_cast<float2*>(e.force)[off + li] = make_float2(fx, fy);
         }
-        if (G == 1) publish_warp_sum(wsum, x, y, active);
+        publish();
+        team_sync();
     }
 
-    if (has_nuc && li < cnt) {
-        reinterpret_cast<float2*>(e.pos)[off + li] = make_float2(x, y);
-        reinterpret_cast<float2*>(e.vel)[off + li] = vel;
-        e.is_proton[off + li] = (tp != 0.f) ? 1 : 0;
-    }
+#pragma unroll
+    for (int k = 0; k < kQ; ++k)
+        if (active && s0 + k < cnt) {
+            reinterpret_cast<float2*>(e.pos)[off + s0 + k] = make_float2(xi[k], yi[k]);
+            reinterpret_cast<float2*>(e.vel)[off + s0 + k] = vi[k];
+            if (e.decay_enabled) e.is_proton[off + s0 + k] = (ti[k] != 0.f) ? 1 : 0;
+        }
     if (leader) {
         e.count[nuc] = cnt;
         if (e.decay_enabled) {
@@ -313,8 +529,12 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------------
-// ensemble_pair_kernel: the production kernel for nuclei of up to 512 nucleons.
+// ensemble_pair_kernel: the block-wide ring, used where the warp-local rings of ensemble_ring_kernel
+// would leave too many lanes idle (Pb-208: 52 subgroups on 2 x 32 lanes = 81 %, against 208 / 224
+// threads = 93 % here; measured on B200, r02: 1.15e12 vs 1.05e12 pairs/s).  See pyqmd_ensemble_step for
+// the dispatch rule.
 //
 // Each thread owns TWO nucleons (2t, 2t+1) of its nucleus, so every evaluation of the law is a
 // packed f32x2 evaluation of (i_a, j) and (i_b, j): all FMA-pipe arithmetic issues as
@@ -333,7 +553,6 @@ __global__ void __launch_bounds__(MAXT) ensemble_kernel(const pyqmd_ensemble e, 
 //   wsum float4[nW]            per-warp position sums (first / second nucleus present in the warp)
 // An odd nucleon count is padded with a ghost neutron parked at (1e5, 1e5): every term of the law
 // is exactly 0 at that distance, so it needs no masking in the pair loop.
-constexpr float kGhost = 1.0e5f;
 
 struct PairSmem {
     float4* A4;
@@ -571,8 +790,13 @@ __global__ void __launch_bounds__(MAXT, PYQMD_ENS_MINBLOCKS) ensemble_pair_kerne
             for (int k = 1; k <= hs; ++k) {
                 visit(t + k, 0);
                 visit(t + k, 1);
+                // lane t - 1 updates the row slot lane t has just written in the next ring step:
+                // order the two accesses (warp-level memory fence; the lanes may not be converged
+                // when a warp spans two nuclei with different counts)
+                __syncwarp(__activemask());
             }
             if (!(m & 1) && t < (m >> 1)) {                 // antipodal super-partner, even m
+                __syncwarp(__activemask());
                 visit(t + (m >> 1), 0);
                 visit(t + (m >> 1), 1);
             }
@@ -657,6 +881,35 @@ static int pick_block_threads(int cap, int* G_out)
 
 using namespace pyqmd;
 
+static const auto ring_single = ensemble_ring_kernel<false, 128, PYQMD_RING_MINBLOCKS_SINGLE>;
+static const auto ring_pair = ensemble_ring_kernel<true, 64, PYQMD_RING_MINBLOCKS_PAIR>;
+static const auto ring_multi = ensemble_ring_kernel<true, 256, 2>;
+
+// cudaFuncSetAttribute is per device: remember which devices have been configured
+static int configure_ensemble_kernels(void)
+{
+    static unsigned char done[64] = {0};
+    static std::mutex mu;
+    int dev = 0;
+    PYQMD_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return PYQMD_OK;
+    const void* kernels[3] = {(const void*)ring_single, (const void*)ring_pair, (const void*)ring_multi};
+    for (const void* k : kernels) {
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
+    }
+    const void* blockwide[2] = {(const void*)ensemble_pair_kernel<224>, (const void*)ensemble_pair_kernel<256>};
+    for (const void* k : blockwide) {
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
+    }
+    if (dev >= 0 && dev < 64) done[dev] = 1;
+    return PYQMD_OK;
+}
+
 extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, void* stream)
 {
     PYQMD_REQUIRE(e != nullptr, "ensemble descriptor is NULL");
@@ -669,58 +922,51 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
     if (n_list == 0 || n_steps == 0) return PYQMD_OK;
     pyqmd_ensemble d = *e;
     d.n_list = n_list;
-    int G = 1;
-    const int T = pick_block_threads(e->cap, &G);
-    const int64_t grid = (n_list + G - 1) / G;
-    PYQMD_REQUIRE(grid <= 2147483647LL, "too many nuclei for one launch");
-    // production path: two nucleons per thread, packed f32x2, Newton-3 ring
-    if (e->cap <= 512) {
+    const LawParams L = make_law_params(e->strong, e->coulomb, e->pauli);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = configure_ensemble_kernels();
+    if (rc != PYQMD_OK) return rc;
+    const RingGeom geo = ring_geom(e->cap);
+    // Which ring?  Lane utilisation decides: warp-local rings (ensemble_ring_kernel) execute ~20 % fewer
+    // instructions per pair, but a nucleus whose 4-nucleon subgroups do not fill its warps (Pb-208:
+    // 26 of 32 lanes) loses more than that; the block-wide ring packs G nuclei into one block instead.
+    // Measured on B200 (r02, pairs/s, ring vs block): U-238 1.21e12 / 1.10e12, Pb-208 1.05 / 1.15,
+    // Au-197 0.98 / 1.08, Ag-107 1.02 / 1.05, Fe-56 0.85 / 0.75, C-14 0.36 / 0.31.
+    bool use_ring = true;
+    if (e->cap > 64 && e->cap <= 512) {
+        const int S = (e->cap + kQ - 1) / kQ;
+        const double u_ring = (double)S / (geo.nG * 32.0);
+        const int capT = (e->cap + 1) / 2;
+        int Gp = 1;
+        const int Tp = pick_block_threads(capT, &Gp);
+        const double u_block = (double)Gp * capT / Tp;
+        use_ring = u_ring >= 0.92 * u_block || pair_smem_bytes(Tp, Gp, capT) > 200 * 1024;
+    }
+    if (!use_ring) {
         const int capT = (e->cap + 1) / 2;
         int Gp = 1;
         const int Tp = pick_block_threads(capT, &Gp);
         const size_t sm = pair_smem_bytes(Tp, Gp, capT);
-        if (sm <= 200 * 1024) {
-            const int64_t gridp = (n_list + Gp - 1) / Gp;
-            PYQMD_REQUIRE(gridp <= 2147483647LL, "too many nuclei for one launch");
-            const LawParams Lp = make_law_params(e->strong, e->coulomb, e->pauli);
-            static bool attr_set = false;
-            if (!attr_set) {
-                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<224>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      200 * 1024));
-                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<224>,
-                                                      cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                      cudaSharedmemCarveoutMaxShared));
-                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<256>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      200 * 1024));
-                PYQMD_CUDA_CHECK(cudaFuncSetAttribute(ensemble_pair_kernel<256>,
-                                                      cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                      cudaSharedmemCarveoutMaxShared));
-                attr_set = true;
-            }
-            // blocks of <= 224 threads: 4 blocks / SM at 72 registers per thread
-            if (Tp <= 224)
-                ensemble_pair_kernel<224><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
-                    d, Lp, n_steps, Gp, capT);
-            else
-                ensemble_pair_kernel<256><<<(unsigned)gridp, Tp, sm, (cudaStream_t)stream>>>(
-                    d, Lp, n_steps, Gp, capT);
-            PYQMD_CUDA_CHECK(cudaGetLastError());
-            return PYQMD_OK;
-        }
+        const int64_t gridp = (n_list + Gp - 1) / Gp;
+        PYQMD_REQUIRE(gridp <= 2147483647LL, "too many nuclei for one launch");
+        // blocks of <= 224 threads: 4 blocks / SM at 72 registers per thread
+        if (Tp <= 224)
+            ensemble_pair_kernel<224><<<(unsigned)gridp, Tp, sm, st>>>(d, L, n_steps, Gp, capT);
+        else
+            ensemble_pair_kernel<256><<<(unsigned)gridp, Tp, sm, st>>>(d, L, n_steps, Gp, capT);
+        PYQMD_CUDA_CHECK(cudaGetLastError());
+        return PYQMD_OK;
     }
-    const int nW = T / 32;
-    const bool n3 = T <= 256;
-    const size_t smem = (size_t)T * (sizeof(float4) + sizeof(float2)) +
-                        (n3 ? (size_t)nW * T * sizeof(float2) : 0) + (size_t)nW * sizeof(float2) +
-                        (size_t)G * sizeof(int);
-    const LawParams L = make_law_params(e->strong, e->coulomb, e->pauli);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n3)
-        ensemble_kernel<256, true><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
+    const int64_t grid = (n_list + geo.G - 1) / geo.G;
+    PYQMD_REQUIRE(grid <= 2147483647LL, "too many nuclei for one launch");
+    const size_t smem = ring_smem_bytes(geo);
+    PYQMD_REQUIRE(smem <= 100 * 1024, "shared memory budget");
+    if (geo.nG == 2)
+        ring_pair<<<(unsigned)grid, 64, smem, st>>>(d, L, n_steps, geo);
+    else if (geo.nG > 2)
+        ring_multi<<<(unsigned)grid, geo.warps * 32, smem, st>>>(d, L, n_steps, geo);
     else
-        ensemble_kernel<1024, false><<<(unsigned)grid, T, smem, st>>>(d, L, n_steps, G);
+        ring_single<<<(unsigned)grid, geo.warps * 32, smem, st>>>(d, L, n_steps, geo);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }

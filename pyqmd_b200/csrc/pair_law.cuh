@@ -99,6 +99,14 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
 }
 __device__ __forceinline__ f32x2 pk1(float v) { return pk(v, v); }
 
+// warp shuffle of a packed pair
+__device__ __forceinline__ f32x2 shfl64(f32x2 v, int src)
+{
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(v & 0xffffffffull), src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((f32x2)hi << 32) | lo;
+}
+
 // General pair: every branch of the law, evaluated with selects (no divergence).
 //   dx,dy  = r_j - r_i                                  [253-254]
 //   ti,tj  = 1.0f for a proton, 0.0f for a neutron
@@ -218,9 +226,22 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     // Coulomb                                                       [284-285]
     net = fma2(mul2(nq, tj2), inv_b, net);
     // Pauli                                                         [288-291]
+#ifdef PYQMD_PAULI_POLY
+    // exp(-d/4) on the FMA pipe: (p6(d))^2, p6 ~ exp(-d/8) minimax on [0, 8] (5.6e-7 relative after
+    // squaring; the value is discarded by the select below for d >= 8).  The general law is bound by
+    // the MUFU pipe (5 per pair, 16/clk/SM), which this takes to 4.
+    f32x2 q = fma2(d, pk1(3.188497021966441e-09f), pk1(-2.323615291288661e-07f));
+    q = fma2(q, d, pk1(1.0052935977000743e-05f));
+    q = fma2(q, d, pk1(-0.0003251763409934938f));
+    q = fma2(q, d, pk1(0.0078120157122612f));
+    q = fma2(q, d, pk1(-0.12499973922967911f));
+    q = fma2(q, d, c.one);
+    const f32x2 netp = fma2(c.negP, mul2(q, q), net);
+#else
     float pa, pb;
     upk(mul2(d, c.kPauli), pa, pb);
     const f32x2 netp = fma2(c.negP, pk(mufu_ex2(pa), mufu_ex2(pb)), net);
+#endif
     float na, nb, npa, npb;
     upk(net, na, nb);
     upk(netp, npa, npb);

@@ -5,11 +5,16 @@
 // (OtsoBear/PyQMD decay_chains.py:400-421, same code as particles.py:126-147) followed, on a
 // hit, by the (Z, N) / half-life part of handle_decay (nuclear_sim.py:213,288-289,353).
 //
-// One thread owns one nucleus for all n_steps sub-steps of a launch (state in registers,
-// HBM read once; written back only for nuclei that actually decayed -- 20 B per nucleus-launch
-// instead of 40).  Draws come from Philox4x32-10 keyed by (seed; global
-// nucleus id, step, slot) or, for the bit-exact parity path, from a caller-supplied array.
-// Per-step decay counts are reduced warp -> block -> one atomicAdd per block and column.
+// One thread owns TWO neighbouring nuclei (global ids 2k, 2k+1) for all n_steps sub-steps of a
+// launch: one Philox4x32-10 call yields both every-step draws (DrawSource, slot 0), which halves the
+// integer work that bounded the round-1 kernel (ncu r01h: ALU 41 %, issue 66 %, HBM 32 %).  State is
+// kept in registers; HBM traffic per nucleus-launch is the 4-byte (Z, N) word: half-life and per-step
+// probability of a tabulated nuclide come from its (L2/L1-resident) table row, the per-nucleus side
+// arrays are read only for nuclides with an ESTIMATED half-life (10**uniform(a, b), one value per
+// nucleus) or when the caller supplied its own per-nucleus values (PYQMD_POP_PER_NUCLEUS_STATE), and
+// written only for nuclei that decayed.  Draws: Philox keyed by (seed; global id, step, slot) or, for
+// the bit-exact parity path, a caller-supplied array.  Per-step decay counts are reduced
+// block-wide -> one atomicAdd per block and column.
 #include "common.cuh"
 #include "decay_device.cuh"
 
@@ -17,58 +22,100 @@ namespace pyqmd {
 
 constexpr int kPopThreads = 256;
 
+struct PopNucleus {
+    int64_t i;        // local index, valid when ok
+    bool ok, dirty;
+    int32_t zn;
+    double T, p;
+};
+
+__device__ __forceinline__ void pop_load(const pyqmd_population& P, PopNucleus& a)
+{
+    a.dirty = false;
+    a.zn = 0; a.T = 0.0; a.p = -1.0;
+    if (!a.ok) return;
+    a.zn = P.zn[a.i];
+    const pyqmd_nuclide_entry* row = lookup(P.table, a.zn);
+    if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || row->kind == PYQMD_HL_BAND) {
+        a.T = P.half_life[a.i];
+        a.p = P.p_decay[a.i];
+    } else {
+        a.T = row->half_life;
+        a.p = row->p_decay;
+    }
+}
+
+// should_decay with the draw u0 (decay_chains.py:400-421) and, on a hit, the (Z, N) / half-life part
+// of handle_decay (nuclear_sim.py:213,288-289,353).  Returns the decay mode that was counted, or NONE.
+__device__ __forceinline__ int pop_step(const pyqmd_population& P, const DrawSource& draws, PopNucleus& a,
+                                        double u0, uint32_t step_abs, int s, bool& fired, int& watch)
+{
+    fired = false;
+    watch = -1;
+    if (!a.ok || !(a.p >= 0.0)) return PYQMD_DECAY_NONE;    // stable: no draw, decay_chains.py:403
+    fired = u0 < a.p;                                       // :421
+    if (!fired) return PYQMD_DECAY_NONE;
+    const uint64_t gid = (uint64_t)(P.id_base + a.i);
+    const pyqmd_nuclide_entry* cur = lookup(P.table, a.zn);
+    int k = 0;
+    if (cur->n_opt > 1) k = pick_option(cur, draws.one(gid, a.i, step_abs, s, 1));   // :218-229
+    const int mode = cur->opt_mode[k];
+    if (mode == PYQMD_DECAY_NONE) return mode;              // :231-232
+    for (int wch = 0; wch < P.n_watch; ++wch)
+        if (P.watch_zn[wch] == a.zn) watch = wch;
+    a.dirty = true;
+    a.zn = cur->opt_zn[k];                                  // nuclear_sim.py:288-289
+    const pyqmd_nuclide_entry* nxt = lookup(P.table, a.zn);
+    const double u3 = (nxt->kind == PYQMD_HL_BAND) ? draws.one(gid, a.i, step_abs, s, 3) : 0.0;
+    bool used3;
+    daughter_half_life(nxt, u3, P.dt_decay, a.T, a.p, used3);                        // nuclear_sim.py:353
+    return mode;
+}
+
 __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_population P,
                                                                  const int n_steps)
 {
     __shared__ unsigned int scount[PYQMD_COUNT_COLS];
-    const int64_t i = (int64_t)blockIdx.x * kPopThreads + threadIdx.x;
-    const bool ok = i < P.n;
-    int32_t zn = 0;
-    double T = 0.0, p = -1.0;
-    if (ok) {
-        zn = P.zn[i];
-        T = P.half_life[i];
-        p = P.p_decay[i];
-    }
+    // global pair index: both nuclei of a pair share one Philox counter, whatever the sharding
+    const int64_t pair = (P.id_base >> 1) + (int64_t)blockIdx.x * kPopThreads + threadIdx.x;
+    PopNucleus a, b;
+    a.i = 2 * pair - P.id_base;
+    b.i = a.i + 1;
+    a.ok = a.i >= 0 && a.i < P.n;
+    b.ok = b.i >= 0 && b.i < P.n;
+    pop_load(P, a);
+    pop_load(P, b);
     const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
-    const uint64_t gid = (uint64_t)(P.id_base + i);
-    bool dirty = false;
 
     for (int s = 0; s < n_steps; ++s) {
         const uint32_t step_abs = P.step0 + (uint32_t)s;
-        bool fired = false;
-        int mode = PYQMD_DECAY_NONE;
-        int watch = -1;
-        if (ok && p >= 0.0) {                               // stable: no draw, decay_chains.py:403
-            double u0, u1;
-            draws.pair(gid, i, step_abs, s, 0, u0, u1);
-            fired = u0 < p;                                 // :421
-            if (fired) {
-                const pyqmd_nuclide_entry* cur = lookup(P.table, zn);
-                const int k = pick_option(cur, u1);         // decay_chains.py:218-229
-                mode = cur->opt_mode[k];
-                if (mode != PYQMD_DECAY_NONE) {             // :231-232
-                    for (int wch = 0; wch < P.n_watch; ++wch)
-                        if (P.watch_zn[wch] == zn) watch = wch;
-                    dirty = true;
-                    zn = cur->opt_zn[k];                    // nuclear_sim.py:288-289
-                    const pyqmd_nuclide_entry* nxt = lookup(P.table, zn);
-                    double u3 = 0.0;
-                    if (nxt->kind == PYQMD_HL_BAND) u3 = draws.one(gid, i, step_abs, s, 3);
-                    bool used3;
-                    daughter_half_life(nxt, u3, P.dt_decay, T, p, used3);   // nuclear_sim.py:353
-                }
-            }
+        double ua = 0.0, ub = 0.0;
+        if (P.uniforms) {
+            if (a.ok) ua = draws.one(0, a.i, step_abs, s, 0);
+            if (b.ok) ub = draws.one(0, b.i, step_abs, s, 0);
+        } else if ((a.ok && a.p >= 0.0) || (b.ok && b.p >= 0.0)) {
+            draws.slot0_pair((uint64_t)pair, step_abs, ua, ub);
         }
-        if (P.decided && ok) P.decided[(int64_t)s * P.n + i] = fired ? 1 : 0;
+        bool fa, fb;
+        int wa, wb;
+        const int ma = pop_step(P, draws, a, ua, step_abs, s, fa, wa);
+        const int mb = pop_step(P, draws, b, ub, step_abs, s, fb, wb);
+        if (P.decided) {
+            if (a.ok) P.decided[(int64_t)s * P.n + a.i] = fa ? 1 : 0;
+            if (b.ok) P.decided[(int64_t)s * P.n + b.i] = fb ? 1 : 0;
+        }
         // block-aggregated counters; one barrier per sub-step when nothing in the block decayed
-        const bool counted = fired && mode != PYQMD_DECAY_NONE;
+        const bool counted = ma != PYQMD_DECAY_NONE || mb != PYQMD_DECAY_NONE;
         if (__syncthreads_or(counted)) {
             if (threadIdx.x < PYQMD_COUNT_COLS) scount[threadIdx.x] = 0;
             __syncthreads();
-            if (counted) {
-                atomicAdd(&scount[mode], 1u);
-                if (watch >= 0) atomicAdd(&scount[8 + watch], 1u);
+            if (ma != PYQMD_DECAY_NONE) {
+                atomicAdd(&scount[ma], 1u);
+                if (wa >= 0) atomicAdd(&scount[8 + wa], 1u);
+            }
+            if (mb != PYQMD_DECAY_NONE) {
+                atomicAdd(&scount[mb], 1u);
+                if (wb >= 0) atomicAdd(&scount[8 + wb], 1u);
             }
             __syncthreads();
             if (threadIdx.x < PYQMD_COUNT_COLS && scount[threadIdx.x] && P.step_counts)
@@ -76,11 +123,8 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
                           (unsigned long long)scount[threadIdx.x]);
         }
     }
-    if (ok && dirty) {
-        P.zn[i] = zn;
-        P.half_life[i] = T;
-        P.p_decay[i] = p;
-    }
+    if (a.ok && a.dirty) { P.zn[a.i] = a.zn; P.half_life[a.i] = a.T; P.p_decay[a.i] = a.p; }
+    if (b.ok && b.dirty) { P.zn[b.i] = b.zn; P.half_life[b.i] = b.T; P.p_decay[b.i] = b.p; }
 }
 
 }  // namespace pyqmd
@@ -90,11 +134,13 @@ using namespace pyqmd;
 extern "C" int pyqmd_population_step(const pyqmd_population* p, int32_t n_steps, void* stream)
 {
     PYQMD_REQUIRE(p != nullptr, "population descriptor is NULL");
-    PYQMD_REQUIRE(n_steps >= 0 && p->n >= 0, "n_steps, n >= 0");
+    PYQMD_REQUIRE(n_steps >= 0 && p->n >= 0 && p->id_base >= 0, "n_steps, n, id_base >= 0");
     if (p->n == 0 || n_steps == 0) return PYQMD_OK;
     PYQMD_REQUIRE(p->zn && p->half_life && p->p_decay && p->table, "state arrays / table");
     PYQMD_REQUIRE(p->n_watch >= 0 && p->n_watch <= 8, "n_watch in [0, 8]");
-    const int64_t blocks = (p->n + kPopThreads - 1) / kPopThreads;
+    // pairs of global ids covered by [id_base, id_base + n): one thread each
+    const int64_t n_pairs = ((p->id_base + p->n + 1) >> 1) - (p->id_base >> 1);
+    const int64_t blocks = (n_pairs + kPopThreads - 1) / kPopThreads;
     PYQMD_REQUIRE(blocks <= 2147483647LL, "population too large for one launch");
     population_kernel<<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps);
     PYQMD_CUDA_CHECK(cudaGetLastError());

@@ -99,6 +99,20 @@ class NuclearForces:
             self.strong_strength, self.coulomb_strength, self.pauli_strength, dt, n_steps)
         _lib.check(rc, "pyqmd_update_particles_f64")
 
+    def step_cloud(self, pos, vel, is_proton, dt, n_steps=1, force=None):
+        """One large system in caller-owned float32 host arrays ``pos[n, 2]``, ``vel[n, 2]`` (numpy or
+        pinned torch CPU tensors, updated in place) and ``is_proton[n]`` (uint8): the reference's
+        per-step call (nuclear_forces.py:185-234) at any N through pyqmd_cloud_step_host -- upload,
+        sort once, ``n_steps`` steps of the symmetric scheme, un-sort, download.  ``force``: optional
+        float32 [n, 2] array receiving the force of the last step."""
+        n = int(pos.shape[0])
+        if n == 0 or n_steps <= 0:
+            return
+        rc = _lib.lib().pyqmd_cloud_step_host(
+            _lib.ptr(pos), _lib.ptr(vel), _lib.ptr(is_proton), _lib.ptr(force), n,
+            self.strong_strength, self.coulomb_strength, self.pauli_strength, dt, n_steps)
+        _lib.check(rc, "pyqmd_cloud_step_host")
+
     def _update_f64(self, particles, dt, n_steps=1):
         n = len(particles)
         x = np.fromiter((p.x for p in particles), np.float64, n)

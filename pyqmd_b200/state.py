@@ -434,14 +434,16 @@ class NucleonCloud:
         ONE kernel per step pulls + sums + clears the accumulators of the rank's block from all
         peers, integrates, and pushes the new positions into all replicas
         (pyqmd_cloud_exchange_integrate), bracketed by two device-side barriers.  No NCCL call on
-        the data path.  Falls back to "nccl" (with a warning) if symmetric memory cannot be set up.
+        the data path.  Raises if symmetric memory cannot be set up, unless
+        ``allow_nccl_fallback=True`` (then "nccl" is used, with a warning); ``self.exchange`` names
+        the exchange that is really in use.
       "nccl": reduce_scatter_tensor(int64 SUM) -> integrate -> all_gather_into_tensor.
     Both exchanges give bit-identical results (integer sums).
     """
 
     def __init__(self, pos, is_proton, vel=None, *, device="cuda", dt=DEFAULT_DT,
                  strengths=DEFAULT_STRENGTHS, rank=0, world=1, group=None, sort=True,
-                 keep_force=False, scheme="symmetric", exchange="peer"):
+                 keep_force=False, scheme="symmetric", exchange="peer", allow_nccl_fallback=False):
         _lib.require_cuda()
         assert scheme in ("symmetric", "ordered") and exchange in ("peer", "nccl")
         dev = self.device = torch.device(device)
@@ -465,7 +467,11 @@ class NucleonCloud:
         if self.exchange == "peer":
             try:
                 self._setup_peer_buffers(padded)
-            except Exception as exc:             # noqa: BLE001 -- any failure: use the NCCL exchange
+            except Exception as exc:             # noqa: BLE001
+                if not allow_nccl_fallback:      # opt-in only: a silent fallback would leave the fused
+                    raise RuntimeError(          # peer-memory kernel untested without anyone noticing
+                        f"symmetric memory unavailable ({exc!r}); pass exchange='nccl' or "
+                        "allow_nccl_fallback=True to use the NCCL exchange") from exc
                 import warnings
                 warnings.warn(f"symmetric memory unavailable ({exc!r}); using the NCCL exchange")
                 self.exchange, self._symm = "nccl", None
@@ -517,7 +523,8 @@ class NucleonCloud:
         _lib.check(_lib.lib().pyqmd_cloud_sort_keys(
             pos.contiguous().data_ptr(), isp.data_ptr(), self.n, float(lo[0]), float(lo[1]),
             extent, keys.data_ptr(), _lib.current_stream()), "pyqmd_cloud_sort_keys")
-        return torch.argsort(keys)
+        # stable: every rank sorts its own replica, equal keys must come out in the same order
+        return torch.argsort(keys, stable=True)
 
     def step(self, n_steps=1):
         lib = _lib.lib()
@@ -564,6 +571,23 @@ class NucleonCloud:
             self.pos, self.pos_next = self.pos_next, self.pos
             self.steps_done += 1
 
+    # -- host-resident state (multi-GPU counterpart of pyqmd_cloud_step_host) ---------------------
+    def download_block(self, h_pos, h_vel):
+        """This rank's block [i0, i1) (sorted order) -> pinned host tensors [i1 - i0, 2]."""
+        h_pos.copy_(self.pos[self.i0:self.i1], non_blocking=True)
+        h_vel.copy_(self.vel[self.i0:self.i1], non_blocking=True)
+        torch.cuda.synchronize(self.device)
+
+    def step_host(self, h_pos, h_vel):
+        """One step with the state of this rank's block in (pinned) HOST memory, the shape of the
+        reference's per-step call (nuclear_forces.py:190-234) on several GPUs: upload the block,
+        all-gather the positions into every replica, step, download the block.  Blocking."""
+        self.pos[self.i0:self.i1].copy_(h_pos, non_blocking=True)
+        self.vel[self.i0:self.i1].copy_(h_vel, non_blocking=True)
+        allgather_positions(self.pos, self.rank, self.world, self.chunk, self.group)
+        self.step(1)
+        self.download_block(h_pos, h_vel)
+
     def pairs_per_step(self):
         """Ordered pairs this rank evaluates per step: (i1 - i0) * (n - 1)."""
         return (self.i1 - self.i0) * (self.n - 1)
@@ -589,7 +613,13 @@ class NucleonCloud:
 # =================================================================================================
 class DecayPopulation:
     """Particle-less nuclei: per sub-step should_decay (decay_chains.py:400-421) and, on a hit,
-    the (Z, N) / half-life update of handle_decay (nuclear_sim.py:213,288-289,353)."""
+    the (Z, N) / half-life update of handle_decay (nuclear_sim.py:213,288-289,353).
+
+    ``half_life`` / ``p_decay``: optional caller-chosen per-nucleus values (then the kernel reads them
+    for every nucleus, 20 B per nucleus and launch); by default they follow get_half_life and the
+    kernel takes the values of tabulated nuclides from the nuclide table (4 B per nucleus and launch)."""
+
+    COUNT_POOL_ROWS = 4096
 
     def __init__(self, zn, *, device="cuda", dt_decay, seed=0, id_base=0, watch=(),
                  half_life=None, p_decay=None, init_seed=0):
@@ -599,6 +629,7 @@ class DecayPopulation:
         check_table_range(self.zn)
         self.n = int(self.zn.numel())
         self.dt_decay, self.seed, self.id_base = float(dt_decay), int(seed), int(id_base)
+        self.per_nucleus_state = half_life is not None or p_decay is not None
         if half_life is None or p_decay is None:
             uniq, inv = torch.unique(self.zn, return_inverse=True)
             Tu, pu = initial_half_lives(uniq.cpu().numpy(), self.dt_decay,
@@ -607,35 +638,60 @@ class DecayPopulation:
             if any(k == _lib.HL_BAND for k in kinds):
                 T, p = initial_half_lives(self.zn.cpu().numpy(), self.dt_decay,
                                           np.random.default_rng(init_seed))
-                half_life, p_decay = torch.from_numpy(T), torch.from_numpy(p)
+                T, p = torch.from_numpy(T), torch.from_numpy(p)
             else:
-                half_life = torch.from_numpy(Tu).to(dev)[inv]
-                p_decay = torch.from_numpy(pu).to(dev)[inv]
+                T = torch.from_numpy(Tu).to(dev)[inv]
+                p = torch.from_numpy(pu).to(dev)[inv]
+            half_life = T if half_life is None else half_life
+            p_decay = p if p_decay is None else p_decay
         self.half_life = torch.as_tensor(half_life, dtype=torch.float64).contiguous().to(dev)
         self.p_decay = torch.as_tensor(p_decay, dtype=torch.float64).contiguous().to(dev)
         self.table = device_table(self.dt_decay, dev)
         self.watch = [nuclides.zn_pack(z, n) for z, n in watch][:8]
         self.step_index = 0
         self._desc = None
+        self._pool, self._pool_used = None, 0
+
+    def _count_rows(self, n_steps):
+        """Zeroed [n_steps, 16] view of a pooled counter buffer: one allocation + fill per
+        COUNT_POOL_ROWS sub-steps instead of one per call (at 8 GPUs a step is ~30 us of kernel)."""
+        if n_steps > self.COUNT_POOL_ROWS:
+            return torch.zeros(n_steps, _lib.COUNT_COLS, dtype=torch.int64, device=self.device)
+        if self._pool is None or self._pool_used + n_steps > self.COUNT_POOL_ROWS:
+            self._pool = torch.zeros(self.COUNT_POOL_ROWS, _lib.COUNT_COLS, dtype=torch.int64,
+                                     device=self.device)
+            self._pool_used = 0
+        out = self._pool[self._pool_used:self._pool_used + n_steps]
+        self._pool_used += n_steps
+        return out
+
+    def bytes_per_nucleus_launch(self):
+        """(HBM bytes the kernel reads per nucleus and launch, explanation) for the roofline."""
+        if self.per_nucleus_state:
+            return 20, "zn + caller-supplied half-life + p (20 B); written back only for decayed nuclei"
+        return 4, ("zn only (4 B): half-life and p of tabulated nuclides come from the cached table row; "
+                   "per-nucleus side arrays are read for estimated half-lives only, written for decayed nuclei")
 
     def step(self, n_steps=1, uniforms=None, want_decisions=False):
         """Returns (counts[n_steps, 16] int64 tensor, decisions[n_steps, n] uint8 or None);
         counts columns: decays by DecayType value 0..7, then decays of watch[k] in 8..15."""
         dev = self.device
-        counts = torch.zeros(n_steps, _lib.COUNT_COLS, dtype=torch.int64, device=dev)
+        counts = self._count_rows(n_steps)
         decided = torch.zeros(n_steps, self.n, dtype=torch.uint8, device=dev) if want_decisions else None
-        if self._desc is None:
-            self._desc = _lib.PopulationDesc()
         if uniforms is not None:
             uniforms = torch.as_tensor(uniforms, dtype=torch.float64).contiguous().to(dev)
             assert tuple(uniforms.shape) == (n_steps, self.n, 4)
+        if self._desc is None:
+            d = self._desc = _lib.PopulationDesc()
+            d.zn, d.half_life, d.p_decay = self.zn.data_ptr(), self.half_life.data_ptr(), self.p_decay.data_ptr()
+            d.n, d.id_base, d.table, d.dt_decay = self.n, self.id_base, self.table.data_ptr(), self.dt_decay
+            d.seed, d.n_watch = self.seed, len(self.watch)
+            d.flags = _lib.POP_PER_NUCLEUS_STATE if self.per_nucleus_state else 0
+            for k, v in enumerate(self.watch):
+                d.watch_zn[k] = v
         d = self._desc
-        d.zn, d.half_life, d.p_decay = self.zn.data_ptr(), self.half_life.data_ptr(), self.p_decay.data_ptr()
-        d.n, d.id_base, d.table, d.dt_decay = self.n, self.id_base, self.table.data_ptr(), self.dt_decay
         d.uniforms, d.uniforms_n = _lib.ptr(uniforms), self.n
-        d.seed, d.step0, d.n_watch = self.seed, self.step_index, len(self.watch)
-        for k, v in enumerate(self.watch):
-            d.watch_zn[k] = v
+        d.step0 = self.step_index
         d.step_counts, d.decided = counts.data_ptr(), _lib.ptr(decided)
         _lib.check(_lib.lib().pyqmd_population_step(C.byref(d), n_steps, _lib.current_stream()),
                    "pyqmd_population_step")

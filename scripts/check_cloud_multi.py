@@ -40,6 +40,21 @@ for scheme, exchange in (("symmetric", "peer"), ("symmetric", "nccl"), ("ordered
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     if rank == 0:
         out[scheme]["replicas_identical"] = bool(same.item())
+# host-resident blocks (NucleonCloud.step_host): upload block -> all-gather -> step -> download block must
+# reproduce the device-resident steps bit for bit
+multi = NucleonCloud(pos, isp, device=f"cuda:{local}", rank=rank, world=world)
+blk = multi.i1 - multi.i0
+h_pos = torch.empty(blk, 2, dtype=torch.float32).pin_memory()
+h_vel = torch.empty(blk, 2, dtype=torch.float32).pin_memory()
+multi.download_block(h_pos, h_vel)
+for _ in range(3):
+    multi.step_host(h_pos, h_vel)
+if rank == 0:
+    single = NucleonCloud(pos, isp, device="cuda:0")
+    single.step(3)
+    out["host_step"] = {"bit_identical": bool(torch.equal(multi.pos[:n], single.pos[:n])
+                                              and torch.equal(h_pos.cuda(), single.pos[multi.i0:multi.i1])),
+                        "exchange_used": multi.exchange}
 if rank == 0:
     print(json.dumps(out))
     for k in ("symmetric_peer", "symmetric_nccl"):

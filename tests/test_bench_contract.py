@@ -17,20 +17,46 @@ def run(*args, env=None):
                           text=True, timeout=600, env=e)
 
 
-def test_reference_arm_prints_one_contract_line():
-    r = run("--impl", "reference", "--steps", "2", "--warmup", "1")
+def _check_reference_line(r, kind):
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "pair interactions/s" and d["unit"] == "pairs/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
-    assert d["value"] > 1e6 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["value"] > 1e5 and d["ms_per_step"] > 0 and d["scaling"] == "strong"
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert "N=1000000" in d["config"]["workload"]          # the headline config: the 1M-nucleon cloud
+    return d
+
+
+def test_reference_arm_times_the_unmodified_reference():
+    """baseline/_ref (baseline/install_reference.py) present: the arm runs the reference's own
+    update_particles_cpu, one process per host core."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref not installed")
+    d = _check_reference_line(run("--impl", "reference", "--steps", "2", "--warmup", "1"), "reference")
+    assert d["value"] < 1e8             # CPython: ~7e5 pairs/s per core
+
+
+def test_reference_arm_falls_back_to_the_port_without_the_reference():
+    r = run("--impl", "reference", "--steps", "2", "--warmup", "1", env={"PYQMD_NO_REF": "1"})
+    _check_reference_line(r, "port")
+
+
+def test_both_arms_describe_the_same_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.parse.__globals__["workload_config"]
+    import argparse
+    ns = argparse.Namespace(workload="cloud", gpus=4, cloud_n=1_000_000, nuclei=0)
+    assert a(ns) == a(ns) and a(ns)["gpus"] == 4
 
 
 def test_reference_arm_other_ranks_exit_without_work():

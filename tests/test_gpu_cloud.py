@@ -291,3 +291,64 @@ def test_random_clouds_against_oracle(seed):
         Fo = np.stack([fx, fy], 1)
         if np.abs(Fo[~amb]).max() > 0:
             assert rel_l2(F, Fo, amb) <= FORCE_TOL, (n, density, frac_p, st, scheme, sort)
+
+
+# ---- host-buffer entry point: pyqmd_cloud_step_host / the large-n branch of pyqmd_update_particles_f64 --
+@pytest.mark.parametrize("n", [1025, 4096, 20000])
+def test_host_buffer_cloud_step_matches_oracle(n):
+    """The reference-shaped call for one large system (nuclear_forces.py:185-234): host arrays in,
+    host arrays out, caller's order kept; force-L2 and position gates against the oracle."""
+    from pyqmd_b200.forces import NuclearForces
+    pos, isp = make_cloud(n, seed=n + 1)
+    rng = np.random.default_rng(n)
+    vel = (rng.standard_normal((n, 2)) * 0.05).astype(np.float32)
+    p, v = pos.copy(), vel.copy()
+    F = np.zeros((n, 2), np.float32)
+    nf = NuclearForces()
+    nf.step_cloud(p, v, isp, 1 / 240, 1, force=F)
+    fx, fy = oracle_forces(pos, isp, 0, n)
+    amb = ambiguous_mask(pos, 0, n) if n <= 4096 else np.zeros(n, bool)
+    Fo = np.stack([fx, fy], 1)
+    assert rel_l2(F.astype(np.float64), Fo, amb) <= FORCE_TOL
+    dt = 1 / 240
+    vw = (vel.astype(np.float64) + Fo * dt) * 0.85
+    want = pos.astype(np.float64) + vw * dt
+    err = np.hypot(*(p.astype(np.float64) - want).T)[~amb].max() / extent_of(pos)
+    assert err <= POS_TOL
+    assert rel_l2(v.astype(np.float64), vw, amb) <= 2e-5
+
+
+def test_host_buffer_cloud_equals_device_resident_steps():
+    """3 steps through the host entry point == 3 steps of the device-resident NucleonCloud (same
+    scheme, same sort keys up to the FP32 rounding of the bounding box), to FP32 rounding."""
+    from pyqmd_b200.forces import NuclearForces
+    from pyqmd_b200.state import NucleonCloud
+    n = 30000
+    pos, isp = make_cloud(n, seed=5)
+    p, v = pos.copy(), np.zeros_like(pos)
+    NuclearForces().step_cloud(p, v, isp, 1 / 240, 3)
+    cloud = NucleonCloud(pos, isp)
+    cloud.step(3)
+    got = cloud.positions().cpu().numpy()
+    assert np.abs(got.astype(np.float64) - p).max() / extent_of(pos) <= 1e-6
+    assert rel_l2(v.astype(np.float64), cloud.velocities().cpu().numpy().astype(np.float64)) <= 1e-5
+
+
+def test_large_system_through_step_arrays_uses_the_sorted_symmetric_scheme():
+    """NuclearForces.step_arrays (float64 state, nuclear_forces.py:236 at N = 200k): force-L2 gate on a
+    sample of nucleons (the oracle evaluates rows [i0, i1) against all partners)."""
+    from pyqmd_b200.forces import NuclearForces
+    n = 200_000
+    pos, isp = make_cloud(n, seed=11)
+    x, y = pos[:, 0].astype(np.float64) + 400.0, pos[:, 1].astype(np.float64) + 400.0
+    vx, vy = np.zeros(n), np.zeros(n)
+    x0, y0 = x.copy(), y.copy()
+    NuclearForces().step_arrays(x, y, vx, vy, isp, 1 / 240, 1)
+    i0, i1 = 70_000, 70_512
+    fx, fy = oracle_forces(pos, isp, i0, i1)
+    dt = 1 / 240
+    Fg = np.stack([vx[i0:i1], vy[i0:i1]], 1) / (0.85 * dt)        # v' = 0.85 F dt from rest
+    assert rel_l2(Fg, np.stack([fx, fy], 1)) <= FORCE_TOL
+    want = np.stack([x0[i0:i1], y0[i0:i1]], 1) + 0.85 * np.stack([fx, fy], 1) * dt * dt
+    err = np.hypot(x[i0:i1] - want[:, 0], y[i0:i1] - want[:, 1]).max() / extent_of(pos)
+    assert err <= POS_TOL

@@ -37,3 +37,7 @@ def test_cloud_schemes_bit_identical_across_gpus(world):
     for k in ("symmetric_peer", "symmetric_nccl", "ordered"):
         assert out[k]["replicas_identical"], k
     assert out["symmetric_peer"]["bit_identical"] and out["symmetric_nccl"]["bit_identical"]
+    # the fused peer-memory kernel really ran (the NCCL fallback is opt-in and was not requested)
+    assert out["symmetric_peer"]["exchange_used"] == "peer"
+    assert out["symmetric_nccl"]["exchange_used"] == "nccl"
+    assert out["host_step"]["bit_identical"], out["host_step"]
