@@ -312,6 +312,49 @@ int pyqmd_ensemble_init_layout(const pyqmd_ensemble *e, const double *shell_radi
 int pyqmd_ensemble_census(const pyqmd_ensemble *e, unsigned long long *counts, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
+/* (C') emitted-particle life cycle (nuclear_sim.py:162,178-210,294-349)                     */
+
+/* One free particle (what the app keeps in self.particles, nuclear_sim.py:349). */
+typedef struct {
+    double x, y, vx, vy;   /* absolute position (origin included), renormalised velocity */
+    double age, lifetime;  /* Particle.age / Particle.lifetime, particles.py:29-38 */
+    int64_t nucleus;       /* global id of the nucleus that emitted it */
+    int32_t type;          /* PYQMD_PT_* */
+    int32_t pad;
+} pyqmd_free_particle;
+
+/* Per-frame constants, computed by the caller with the reference's own expressions (they depend on
+ * the frame only, not on the particle): see pyqmd_b200/sim.py:frame_constants. */
+typedef struct {
+    int32_t num_steps;      /* sub-steps of the frame = update_particle calls per particle, :153,162 */
+    uint32_t step0;         /* ensemble step index of the frame's first sub-step */
+    int32_t fast_forward;   /* time_scale > 1.0, :320 */
+    int32_t reserved;
+    double speed_scale;     /* 0.3 * (10 / max(1, substeps_used)), :189-190 */
+    double aging_scale;     /* min(1, 1 / (sqrt(max(1, ts/100)) * sqrt(max(1, sub/10)))), :199-200 */
+    double age_dt;          /* desired_dt / num_steps, :162 */
+    double nucleon_dt;      /* effective_physics_dt * time_scale ** 0.5, :207 */
+    double lifetime_fast;   /* lifetime of every product when time_scale > 1, :320-338 */
+    double lifetime_floor;  /* 5 * max(1, substeps_used / 5), :341 */
+} pyqmd_free_frame;
+
+/*
+ * One frame of the free-particle list: (1) every particle of pool_in[0 .. *n_in) is advanced by
+ * frame->num_steps update_particle calls (nuclear_sim.py:178-210) and, unless it expired, appended to
+ * pool_out; (2) every decay event of events[0 .. *event_count) with an emitted particle gets the speed /
+ * lifetime rewrite of handle_decay (:295-342), the sub-steps that were left in its frame, and is
+ * appended as well; (3) *event_count is reset when reset_event_count != 0.  *n_out is the new length
+ * (particles beyond `capacity` are counted in *dropped).  All counts are DEVICE counters: the host
+ * never synchronises.  The order of pool_out is unspecified.
+ */
+int pyqmd_free_particles_frame(const pyqmd_free_particle *pool_in, const unsigned long long *n_in,
+                               pyqmd_free_particle *pool_out, unsigned long long *n_out,
+                               int64_t capacity, const pyqmd_decay_event *events,
+                               unsigned long long *event_count, int64_t event_capacity,
+                               const pyqmd_free_frame *frame, unsigned long long *dropped,
+                               int32_t reset_event_count, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
 /* (D) decay-only population of particle-less nuclei (decay_chains.py:390-421; config 5)     */
 
 #define PYQMD_COUNT_COLS 16   /* per step: decays by mode [0..7], decays of watch_zn[k] [8..15] */

@@ -28,7 +28,7 @@ EXPORTS = (
     "pyqmd_cloud_exchange_integrate",
     "pyqmd_ensemble_step", "pyqmd_ensemble_step_host", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
     "pyqmd_ensemble_init_layout",
-    "pyqmd_population_step",
+    "pyqmd_population_step", "pyqmd_free_particles_frame",
 )
 
 # numpy mirror of pyqmd_nuclide_entry (80 bytes)
@@ -43,7 +43,12 @@ EVENT_DTYPE = np.dtype([
     ("nucleus", "<i8"), ("step", "<i4"), ("mode", "<i4"), ("zn_new", "<i4"), ("ptype", "<i4"),
     ("x", "<f8"), ("y", "<f8"), ("vx", "<f8"), ("vy", "<f8"),
 ], align=True)
-assert NUCLIDE_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 56
+# numpy mirror of pyqmd_free_particle (64 bytes)
+FREE_DTYPE = np.dtype([
+    ("x", "<f8"), ("y", "<f8"), ("vx", "<f8"), ("vy", "<f8"), ("age", "<f8"), ("lifetime", "<f8"),
+    ("nucleus", "<i8"), ("type", "<i4"), ("pad", "<i4"),
+], align=True)
+assert NUCLIDE_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 56 and FREE_DTYPE.itemsize == 64
 
 
 class EnsembleDesc(C.Structure):
@@ -92,6 +97,15 @@ class PopulationDesc(C.Structure):
 POP_PER_NUCLEUS_STATE = 1
 
 
+class FreeFrame(C.Structure):
+    """pyqmd_free_frame"""
+    _fields_ = [
+        ("num_steps", C.c_int32), ("step0", C.c_uint32), ("fast_forward", C.c_int32), ("reserved", C.c_int32),
+        ("speed_scale", C.c_double), ("aging_scale", C.c_double), ("age_dt", C.c_double),
+        ("nucleon_dt", C.c_double), ("lifetime_fast", C.c_double), ("lifetime_floor", C.c_double),
+    ]
+
+
 _lib = None
 
 
@@ -130,6 +144,7 @@ def lib():
     L.pyqmd_ensemble_init_layout.argtypes = [C.POINTER(EnsembleDesc), C.POINTER(C.c_double), vp,
                                              C.c_uint64, vp]
     L.pyqmd_population_step.argtypes = [C.POINTER(PopulationDesc), i32, vp]
+    L.pyqmd_free_particles_frame.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, C.POINTER(FreeFrame), vp, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("pyqmd_last_error", "pyqmd_cloud_workspace_bytes"):

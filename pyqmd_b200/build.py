@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpyqmd_b200.so")
-SOURCES = ["api.cu", "cloud.cu", "cloud_host.cu", "cloud_sym.cu", "ensemble.cu", "layout.cu", "overlaps.cu", "population.cu"]
+SOURCES = ["api.cu", "cloud.cu", "cloud_host.cu", "cloud_sym.cu", "ensemble.cu", "free_particles.cu", "layout.cu", "overlaps.cu", "population.cu"]
 HEADERS = ["common.cuh", "pair_law.cuh", "cloud.cuh", "decay_device.cuh", "../../include/pyqmd_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -275,6 +275,7 @@ extern "C" int pyqmd_device_props(int device, int64_t out[8])
 
 extern "C" int pyqmd_struct_sizes(int64_t out[4])
 {
+    static_assert(sizeof(pyqmd_free_particle) == 64 && sizeof(pyqmd_free_frame) == 64, "ABI layout");
     PYQMD_REQUIRE(out != nullptr, "out is NULL");
     out[0] = sizeof(pyqmd_nuclide_entry);
     out[1] = sizeof(pyqmd_decay_event);

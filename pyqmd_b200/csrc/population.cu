@@ -23,11 +23,17 @@ namespace pyqmd {
 constexpr int kPopThreads = 256;
 
 struct PopNucleus {
-    int64_t i;        // local index, valid when ok
+    int i;            // local index, valid when ok (populations are < 2^31 nuclei per GPU)
     bool ok, dirty;
     int32_t zn;
-    double T, p;
+    double T, p;      // T is only defined after a decay in this launch (it is never read before)
 };
+
+// table row of an in-range (Z, N): callers validate on the host, daughters come from the table
+__device__ __forceinline__ const pyqmd_nuclide_entry* row_of(const pyqmd_nuclide_entry* table, int32_t zn)
+{
+    return table + ((zn >> 16) * PYQMD_TABLE_NDIM + (zn & 0xffff));
+}
 
 __device__ __forceinline__ void pop_load(const pyqmd_population& P, PopNucleus& a)
 {
@@ -35,14 +41,11 @@ __device__ __forceinline__ void pop_load(const pyqmd_population& P, PopNucleus& 
     a.zn = 0; a.T = 0.0; a.p = -1.0;
     if (!a.ok) return;
     a.zn = P.zn[a.i];
-    const pyqmd_nuclide_entry* row = lookup(P.table, a.zn);
-    if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || row->kind == PYQMD_HL_BAND) {
-        a.T = P.half_life[a.i];
+    const pyqmd_nuclide_entry* row = row_of(P.table, a.zn);
+    if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || row->kind == PYQMD_HL_BAND)
         a.p = P.p_decay[a.i];
-    } else {
-        a.T = row->half_life;
+    else
         a.p = row->p_decay;
-    }
 }
 
 // should_decay with the draw u0 (decay_chains.py:400-421) and, on a hit, the (Z, N) / half-life part
@@ -56,7 +59,7 @@ __device__ __forceinline__ int pop_step(const pyqmd_population& P, const DrawSou
     fired = u0 < a.p;                                       // :421
     if (!fired) return PYQMD_DECAY_NONE;
     const uint64_t gid = (uint64_t)(P.id_base + a.i);
-    const pyqmd_nuclide_entry* cur = lookup(P.table, a.zn);
+    const pyqmd_nuclide_entry* cur = row_of(P.table, a.zn);
     int k = 0;
     if (cur->n_opt > 1) k = pick_option(cur, draws.one(gid, a.i, step_abs, s, 1));   // :218-229
     const int mode = cur->opt_mode[k];
@@ -77,12 +80,14 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
 {
     __shared__ unsigned int scount[PYQMD_COUNT_COLS];
     // global pair index: both nuclei of a pair share one Philox counter, whatever the sharding
-    const int64_t pair = (P.id_base >> 1) + (int64_t)blockIdx.x * kPopThreads + threadIdx.x;
+    const int j = (int)(blockIdx.x * kPopThreads + threadIdx.x);
+    const uint64_t pair = (uint64_t)(P.id_base >> 1) + (uint64_t)j;
+    const int n = (int)P.n;
     PopNucleus a, b;
-    a.i = 2 * pair - P.id_base;
+    a.i = 2 * j - (int)(P.id_base & 1);
     b.i = a.i + 1;
-    a.ok = a.i >= 0 && a.i < P.n;
-    b.ok = b.i >= 0 && b.i < P.n;
+    a.ok = a.i >= 0 && a.i < n;
+    b.ok = b.i < n;
     pop_load(P, a);
     pop_load(P, b);
     const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
@@ -94,15 +99,15 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
             if (a.ok) ua = draws.one(0, a.i, step_abs, s, 0);
             if (b.ok) ub = draws.one(0, b.i, step_abs, s, 0);
         } else if ((a.ok && a.p >= 0.0) || (b.ok && b.p >= 0.0)) {
-            draws.slot0_pair((uint64_t)pair, step_abs, ua, ub);
+            draws.slot0_pair(pair, step_abs, ua, ub);
         }
         bool fa, fb;
         int wa, wb;
         const int ma = pop_step(P, draws, a, ua, step_abs, s, fa, wa);
         const int mb = pop_step(P, draws, b, ub, step_abs, s, fb, wb);
         if (P.decided) {
-            if (a.ok) P.decided[(int64_t)s * P.n + a.i] = fa ? 1 : 0;
-            if (b.ok) P.decided[(int64_t)s * P.n + b.i] = fb ? 1 : 0;
+            if (a.ok) P.decided[(int64_t)s * n + a.i] = fa ? 1 : 0;
+            if (b.ok) P.decided[(int64_t)s * n + b.i] = fb ? 1 : 0;
         }
         // block-aggregated counters; one barrier per sub-step when nothing in the block decayed
         const bool counted = ma != PYQMD_DECAY_NONE || mb != PYQMD_DECAY_NONE;
@@ -135,6 +140,7 @@ extern "C" int pyqmd_population_step(const pyqmd_population* p, int32_t n_steps,
 {
     PYQMD_REQUIRE(p != nullptr, "population descriptor is NULL");
     PYQMD_REQUIRE(n_steps >= 0 && p->n >= 0 && p->id_base >= 0, "n_steps, n, id_base >= 0");
+    PYQMD_REQUIRE(p->n < 2147483647LL / 2, "at most 2^30 nuclei per launch");
     if (p->n == 0 || n_steps == 0) return PYQMD_OK;
     PYQMD_REQUIRE(p->zn && p->half_life && p->p_decay && p->table, "state arrays / table");
     PYQMD_REQUIRE(p->n_watch >= 0 && p->n_watch <= 8, "n_watch in [0, 8]");

@@ -9,12 +9,16 @@ of the hot path, without pygame.
     sim.decay_counts                            # populated (the reference never increments it)
     sim.free_particles                          # emitted alpha/e-/e+/gamma still alive
 
-Frame logic mirrored here, on the host, with the reference's formulas:
-  sub-step plan                    nuclear_sim.py:123-153   -> ``substep_plan``
+Frame logic:
+  sub-step plan                    nuclear_sim.py:123-153   -> ``substep_plan`` (host)
   sub-step loop                    :161-173                 -> NucleusEnsemble.step (device)
-  overlap projection once a frame  :175-176, :355-379       -> NucleusEnsemble.resolve_overlaps
-  emitted particle speed/lifetime  :295-342                 -> ``cosmetic_speed_lifetime``
-  free particle animation          :178-210                 -> ``animate``
+  overlap projection once a frame  :175-176, :355-379       -> NucleusEnsemble.resolve_overlaps (device)
+  emitted particle speed/lifetime  :295-342                 -> ``FreeParticlePool`` (device,
+  free particle animation          :178-210                    pyqmd_free_particles_frame)
+A frame issues kernels only: nothing is read back unless the caller asks for ``decay_counts`` or
+``free_particles``.  ``cosmetic_speed_lifetime`` / ``animate`` are the host mirrors of the two device
+kernels; the CPU test-suite pins them bit for bit to goldens generated from the reference, the GPU
+suite compares the device pool with them.
 """
 from __future__ import annotations
 
@@ -22,6 +26,7 @@ import math
 
 import numpy as np
 
+from . import _lib
 from .types import DecayType, ParticleType
 
 _ANIMATED = (ParticleType.ALPHA.value, ParticleType.ELECTRON.value, ParticleType.GAMMA.value,
@@ -129,11 +134,76 @@ def animate(ptype, x, y, vx, vy, age, lifetime, dt, age_dt, time_scale, substeps
     return x, y, age, alive
 
 
+def frame_constants(time_scale, num_steps, eff_dt, step_time, physics_dt, step0=0):
+    """Per-frame constants of the free-particle update (pyqmd_free_frame), evaluated with the
+    reference's expressions (nuclear_sim.py:189-190,199-200,207,320-341) in Python float64."""
+    f = _lib.FreeFrame()
+    f.num_steps, f.step0 = int(num_steps), int(step0) & 0xFFFFFFFF
+    f.fast_forward = 1 if time_scale > 1.0 else 0
+    f.speed_scale = 0.3 * (10.0 / max(1.0, num_steps))
+    f.aging_scale = min(1.0, 1.0 / (math.sqrt(max(1.0, time_scale / 100.0)) *
+                                    math.sqrt(max(1.0, num_steps / 10.0))))
+    f.age_dt = step_time
+    f.nucleon_dt = eff_dt * (time_scale ** 0.5)
+    f.lifetime_fast = 0.0
+    if time_scale > 1.0:            # the same for every particle type (:320-338)
+        f.lifetime_fast = cosmetic_speed_lifetime(ParticleType.ALPHA.value, 1.0, 0.0, time_scale, num_steps,
+                                                  physics_dt)[2]
+    f.lifetime_floor = 5.0 * max(1.0, num_steps / 5.0)
+    return f
+
+
+class FreeParticlePool:
+    """The app's ``self.particles`` (nuclear_sim.py:349) for a whole ensemble, on the device: two
+    ping-pong arrays of pyqmd_free_particle and device-side counters.  ``frame`` advances the pool by
+    one app frame and absorbs the ensemble's decay events of that frame; it never synchronises."""
+
+    def __init__(self, device, capacity=1 << 20):
+        import torch
+        self.device, self.capacity = torch.device(device), int(capacity)
+        nbytes = self.capacity * _lib.FREE_DTYPE.itemsize
+        self.buf = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.count = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.dropped = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.cur = 0
+
+    def frame(self, ens, frame: "_lib.FreeFrame", reset_event_count=True):
+        import ctypes as C
+
+        import torch
+        a, b = self.cur, self.cur ^ 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pyqmd_free_particles_frame(
+                self.buf[a].data_ptr(), self.count[a].data_ptr(), self.buf[b].data_ptr(),
+                self.count[b].data_ptr(), self.capacity, _lib.ptr(ens.events_buf) if ens is not None else None,
+                _lib.ptr(ens.event_count) if ens is not None else None,
+                ens.event_capacity if ens is not None else 0, C.byref(frame), self.dropped.data_ptr(),
+                1 if reset_event_count else 0, _lib.current_stream()), "pyqmd_free_particles_frame")
+        self.cur = b
+
+    def load(self, records):
+        """Replace the pool by ``records`` (structured numpy array, _lib.FREE_DTYPE)."""
+        import torch
+        rec = np.ascontiguousarray(records, dtype=_lib.FREE_DTYPE)
+        assert len(rec) <= self.capacity
+        raw = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy())
+        self.buf[self.cur][: raw.numel()].copy_(raw)
+        self.count[self.cur].fill_(len(rec))
+
+    def download(self):
+        """The live particles as a structured numpy array sorted by (nucleus, type, x) -- the device
+        order is unspecified."""
+        n = min(int(self.count[self.cur].item()), self.capacity)
+        raw = self.buf[self.cur][: n * _lib.FREE_DTYPE.itemsize].cpu().numpy()
+        rec = raw.view(_lib.FREE_DTYPE).copy()
+        return rec[np.lexsort((rec["x"], rec["type"], rec["nucleus"]))]
+
+
 class HeadlessSimulation:
     """N copies of the reference's single-nucleus simulation, stepped frame by frame on the GPU."""
 
     def __init__(self, isotope=(92, 146), n_nuclei=1, *, isotopes=None, device="cuda", seed=0,
-                 time_scale=1.0, origin=(400.0, 400.0), rotate=True):
+                 time_scale=1.0, origin=(400.0, 400.0), rotate=True, free_capacity=1 << 20):
         from .state import NucleusEnsemble
         self.isotopes = tuple(isotopes) if isotopes else (tuple(isotope),)
         self.physics_dt = 1.0 / 240.0           # nuclear_sim.py:59
@@ -145,24 +215,46 @@ class HeadlessSimulation:
         self.time_passed = 0.0                  # :54
         self.substeps_used = 0                  # :64
         self.frames = 0
-        self.decay_counts = {d.name: 0 for d in DecayType if d != DecayType.NONE}   # :56
         org = np.tile(np.asarray(origin, np.float64), (n_nuclei, 1))                # :93
         self.ensemble = NucleusEnsemble.from_templates(self.isotopes, n_nuclei, device=device,
                                                        seed=seed, origin=org, rotate=rotate,
                                                        dt_decay=1.0 / 240.0)
-        self._events_seen = 0
-        self.events_dropped = 0
-        # free (emitted) particles, SoA on the host: few and short-lived
-        self.free = {k: np.zeros(0) for k in ("x", "y", "vx", "vy", "age", "lifetime")}
-        self.free["type"] = np.zeros(0, np.int32)
-        self.free["nucleus"] = np.zeros(0, np.int64)
+        # free (emitted) particles live on the device (nuclear_sim.py:349 keeps them in a list)
+        self.pool = FreeParticlePool(self.ensemble.device, free_capacity)
+
+    # -- lazily read-back views (the only places that synchronise) --------------------------------------
+    @property
+    def decay_counts(self):
+        """Decays so far by DecayType name (:56; the reference initialises and renders this dict but
+        never increments it) -- read from the device counters on demand."""
+        mc = self.ensemble.mode_counts.cpu().tolist()
+        return {d.name: int(mc[d.value]) for d in DecayType if d != DecayType.NONE}
+
+    @property
+    def events_dropped(self):
+        """Emitted particles lost because the pool overflowed (the event log is drained every frame;
+        events beyond its capacity within ONE frame are counted in decay_counts but get no particle)."""
+        return int(self.pool.dropped.item())
+
+    @property
+    def _events_seen(self):
+        return int(self.ensemble.mode_counts.sum().item())
 
     @property
     def free_particles(self):
-        return self.free
+        """The emitted particles still alive, SoA on the host (downloaded on demand)."""
+        rec = self.pool.download()
+        out = {k: rec[k].astype(np.float64) for k in ("x", "y", "vx", "vy", "age", "lifetime")}
+        out["type"] = rec["type"].astype(np.int32)
+        out["nucleus"] = rec["nucleus"].astype(np.int64)
+        return out
+
+    @property
+    def free(self):
+        return self.free_particles
 
     def update_simulation(self, dt):
-        """One frame (nuclear_sim.py:118-176)."""
+        """One frame (nuclear_sim.py:118-176): kernels only, no read-back."""
         num_steps, eff_dt, step_time, self.physics_dt = substep_plan(
             dt, self.time_scale, self.physics_dt, self.accuracy, self.max_substeps,
             self.auto_adjust_substeps, self.physics_dt_factor)
@@ -174,56 +266,11 @@ class HeadlessSimulation:
         step0 = ens.step_index
         ens.step(num_steps)                                                 # :161-173
         ens.resolve_overlaps()                                              # :175-176
-        # free particles already alive: one animation update per sub-step (:162)
-        self.free = self._animate(self.free, num_steps, eff_dt, step_time, num_steps)
-        # this frame's emissions (:349): a particle emitted in sub-step s is animated by the
-        # remaining sub-steps s+1 .. num_steps-1 of the frame
-        self._collect_events(num_steps, step0, eff_dt, step_time)
+        # free particles: those already alive get one update per sub-step (:162); this frame's emissions
+        # (:349) get the speed / lifetime rewrite (:295-342) and the sub-steps left after their own
+        self.pool.frame(ens, frame_constants(self.time_scale, num_steps, eff_dt, step_time, self.physics_dt,
+                                             step0))
         self.frames += 1
-
-    def _animate(self, f, n_updates, eff_dt, step_time, num_steps):
-        n_updates = np.broadcast_to(np.asarray(n_updates), f["x"].shape)
-        for k in range(int(n_updates.max()) if len(f["x"]) else 0):
-            x, y, age, alive = animate(f["type"], f["x"], f["y"], f["vx"], f["vy"], f["age"],
-                                       f["lifetime"], eff_dt, step_time, self.time_scale, num_steps)
-            todo = n_updates > k
-            f["x"] = np.where(todo, x, f["x"])
-            f["y"] = np.where(todo, y, f["y"])
-            f["age"] = np.where(todo, age, f["age"])
-            keep = alive | ~todo
-            if not keep.all():
-                f = {key: v[keep] for key, v in f.items()}
-                n_updates = n_updates[keep]
-        return f
-
-    def _collect_events(self, num_steps, step0=0, eff_dt=1.0 / 240.0, step_time=1.0 / 240.0):
-        ens = self.ensemble
-        total = int(ens.event_count.item())
-        mc = ens.mode_counts.cpu().tolist()
-        for d in DecayType:
-            if d != DecayType.NONE:
-                self.decay_counts[d.name] = int(mc[d.value])
-        if total == 0:
-            return
-        # the device log holds this frame's events only: it is drained (cursor reset) every frame, so
-        # long runs never overflow it; events beyond its capacity within ONE frame are counted in
-        # decay_counts but get no free particle
-        new = ens.events()                       # sorted by (step, nucleus)
-        self.events_dropped += max(0, total - len(new))
-        ens.event_count.zero_()
-        self._events_seen += total
-        new = new[new["ptype"] >= 0]
-        if len(new) == 0:
-            return
-        vx, vy, life = cosmetic_speed_lifetime_array(new["ptype"], new["vx"], new["vy"], self.time_scale,
-                                                     num_steps, self.physics_dt)
-        born = dict(x=new["x"].astype(np.float64), y=new["y"].astype(np.float64),
-                    vx=vx, vy=vy, age=np.zeros(len(new)),
-                    lifetime=life, type=new["ptype"].astype(np.int32),
-                    nucleus=new["nucleus"].astype(np.int64))
-        remaining = np.clip(num_steps - 1 - (new["step"].astype(np.int64) - step0), 0, num_steps)
-        born = self._animate(born, remaining, eff_dt, step_time, num_steps)
-        self.free = {k: np.concatenate([self.free[k], born[k]]) for k in self.free}
 
     def free_particle_objects(self, k=None):
         """The emitted particles still alive as ``Particle`` objects (what the app keeps in

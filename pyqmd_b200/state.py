@@ -15,6 +15,7 @@ sub-step (nuclear_forces.py:190-234).  Here the state never leaves HBM between s
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 import os
 
@@ -34,6 +35,16 @@ CODE_ISOTOPES = ((1, 2), (2, 3), (6, 8), (8, 9), (26, 33), (47, 61), (79, 119), 
 
 _TEMPLATES = None
 _TABLE_CACHE = {}
+
+
+def _on_device(fn):
+    """Run a method with ``self.device`` as the current CUDA device: the C ABI launches on the
+    current device's stream, so pointers of another device must never meet it."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 def layout_templates():
@@ -216,6 +227,7 @@ class NucleusEnsemble:
         ens.init_layout(layout_seed, layout_uniforms)
         return ens
 
+    @_on_device
     def init_layout(self, seed=0, uniforms=None):
         """(Re)generate the initial layout of every nucleus on the device (particles.py:62-124)."""
         lib = _lib.lib()
@@ -256,6 +268,7 @@ class NucleusEnsemble:
         d.event_count, d.mode_counts = self.event_count.data_ptr(), self.mode_counts.data_ptr()
         return d
 
+    @_on_device
     def set_dt_decay(self, dt_decay):
         """Change the dt ``should_decay`` sees (nuclear_sim.py:165: it varies from frame to frame
         with the time scale).  Per-nucleus probabilities are recomputed on the host from the
@@ -266,16 +279,16 @@ class NucleusEnsemble:
             return
         self.dt_decay = dt_decay
         self.table = device_table(dt_decay, self.device)
-        uniq, inv = torch.unique(self.half_life, return_inverse=True)
-        pu = np.array([nuclides.decay_probability(float(t), dt_decay) for t in uniq.cpu().tolist()],
-                      np.float64)
-        self.p_decay.copy_(torch.from_numpy(pu).to(self.device)[inv])
+        p = nuclides.decay_probabilities(self.half_life.cpu().numpy(), dt_decay)
+        self.p_decay.copy_(torch.from_numpy(p))
 
+    @_on_device
     def launch(self, cap, lst_ptr, n_list, n_steps, stream, uniforms=None):
         d = self._desc(cap, None, n_list, uniforms)
         d.list = lst_ptr
         _lib.check(_lib.lib().pyqmd_ensemble_step(C.byref(d), n_steps, stream), "pyqmd_ensemble_step")
 
+    @_on_device
     def step(self, n_steps=1, uniforms=None):
         """``n_steps`` sub-steps of every nucleus (nuclear_sim.py:161-173).  ``uniforms``:
         optional float64 tensor [n_steps, n_nuclei, 4] of draws (slots of SURVEY.md section 8a)
@@ -291,6 +304,7 @@ class NucleusEnsemble:
         self.step_index += n_steps
         return len(self.bins)
 
+    @_on_device
     def resolve_overlaps(self, uniforms=None):
         """Per-frame projection NuclearSimulation.resolve_overlaps (nuclear_sim.py:355-379) for
         every nucleus.  ``uniforms``: optional float64 [n_nuclei, k] draws for the degenerate
@@ -316,6 +330,7 @@ class NucleusEnsemble:
         self.step(n_substeps, uniforms)
         self.resolve_overlaps()
 
+    @_on_device
     def census(self, sample=None):
         """Branch census of the pair law (device kernel) over ``sample`` (iterable of nucleus
         indices, default all).  Returns (counts dict, algorithmic FLOPs per ordered pair by the
@@ -369,6 +384,7 @@ class HostEnsembleRunner:
 
     def __init__(self, ens: NucleusEnsemble, chunks=8):
         self.ens = ens
+        self.device = ens.device
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         self.h_pos, self.h_vel, self.h_isp = pin(ens.pos), pin(ens.vel), pin(ens.is_proton)
         self.h_count, self.h_zn = pin(ens.count), pin(ens.zn)
@@ -406,6 +422,7 @@ class HostEnsembleRunner:
         self.d2h_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes) + (
             int(self.h_isp.nbytes + self.h_count.nbytes + self.h_zn.nbytes) if ens.decay else 0)
 
+    @_on_device
     def step(self, n_steps=1):
         ens = self.ens
         d = ens._desc(1, None, 0, None)
@@ -516,6 +533,7 @@ class NucleonCloud:
         torch.cuda.synchronize(dev)
         hdls["acc"].barrier(channel=0)           # every rank's buffers are zeroed before the first step
 
+    @_on_device
     def _sort_perm(self, pos, isp):
         lo = pos.min(0).values
         extent = float((pos.max(0).values - lo).max().item()) * 1.0001 + 1e-6
@@ -526,6 +544,7 @@ class NucleonCloud:
         # stable: every rank sorts its own replica, equal keys must come out in the same order
         return torch.argsort(keys, stable=True)
 
+    @_on_device
     def step(self, n_steps=1):
         lib = _lib.lib()
         S, Cc, P = self.strengths
@@ -572,12 +591,14 @@ class NucleonCloud:
             self.steps_done += 1
 
     # -- host-resident state (multi-GPU counterpart of pyqmd_cloud_step_host) ---------------------
+    @_on_device
     def download_block(self, h_pos, h_vel):
         """This rank's block [i0, i1) (sorted order) -> pinned host tensors [i1 - i0, 2]."""
         h_pos.copy_(self.pos[self.i0:self.i1], non_blocking=True)
         h_vel.copy_(self.vel[self.i0:self.i1], non_blocking=True)
         torch.cuda.synchronize(self.device)
 
+    @_on_device
     def step_host(self, h_pos, h_vel):
         """One step with the state of this rank's block in (pinned) HOST memory, the shape of the
         reference's per-step call (nuclear_forces.py:190-234) on several GPUs: upload the block,
@@ -672,6 +693,7 @@ class DecayPopulation:
         return 4, ("zn only (4 B): half-life and p of tabulated nuclides come from the cached table row; "
                    "per-nucleus side arrays are read for estimated half-lives only, written for decayed nuclei")
 
+    @_on_device
     def step(self, n_steps=1, uniforms=None, want_decisions=False):
         """Returns (counts[n_steps, 16] int64 tensor, decisions[n_steps, n] uint8 or None);
         counts columns: decays by DecayType value 0..7, then decays of watch[k] in 8..15."""

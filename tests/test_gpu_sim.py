@@ -111,3 +111,109 @@ def test_render_bridge_feeds_the_reference_renderer_signature():
     assert gpu_available is True and substeps == sim.substeps_used and max_substeps == 20
     assert set(decay_counts) == {d.name for d in DecayType if d != DecayType.NONE}
     assert time_passed == sim.time_passed and time_scale == sim.time_scale
+
+
+# ---- emitted-particle life cycle on the device (pyqmd_free_particles_frame) ---------------------------
+def _free_records(rows):
+    from pyqmd_b200 import _lib
+    rec = np.zeros(len(rows), _lib.FREE_DTYPE)
+    for k, r in enumerate(rows):
+        for key, v in r.items():
+            rec[k][key] = v
+    return rec
+
+
+def test_free_particle_animation_matches_reference_goldens():
+    """update_particle (nuclear_sim.py:178-210) on the device against goldens generated from the
+    reference (tests/golden/sim_driver.json.gz, `animation`): six updates of one particle per case."""
+    from conftest import load_json
+    from pyqmd_b200.sim import FreeParticlePool, frame_constants
+    gold = load_json("sim_driver.json.gz")["animation"]
+    fh = float.fromhex
+    pool = FreeParticlePool("cuda", capacity=64)
+    for row in gold:
+        ts, sub, ptype = fh(row["time_scale"]), row["substeps"], row["ptype"]
+        life = 0.05 if ptype != ParticleType.NEUTRON.value else float("inf")
+        p = dict(x=1.0, y=-2.0, vx=30.0, vy=-40.0, age=0.0, lifetime=life, nucleus=7, type=ptype)
+        alive = []
+        pool.load(_free_records([p]))
+        for k in range(6):
+            # one update_particle(p, 1/240, 0.004 * (k + 1)) with substeps_used = sub: a "frame" of 1 update
+            f = frame_constants(ts, sub, 1 / 240, 0.004 * (k + 1), 1 / 240)
+            f.num_steps = 1
+            pool.frame(None, f)
+            rec = pool.download()
+            alive.append(len(rec) == 1)
+            if len(rec) == 1:
+                last = rec[0].copy()
+            else:
+                break
+        # the reference keeps updating the object after it expired; compare up to the first expiry
+        first_dead = row["alive"].index(False) if False in row["alive"] else None
+        assert alive == row["alive"][: len(alive)], row
+        if first_dead is None:
+            assert (last["x"], last["y"], last["age"]) == (fh(row["x"]), fh(row["y"]), fh(row["age"])), row
+
+
+def test_free_particle_pool_follows_the_host_mirror_over_frames():
+    """A C-14 ensemble decaying over many frames: the device pool (speed / lifetime rewrite of
+    handle_decay :295-342, per-sub-step animation and expiry :178-210, births mid-frame) equals the
+    host mirror of pyqmd_b200.sim -- which the CPU suite pins bit for bit to the reference goldens --
+    applied to the same device event log."""
+    from pyqmd_b200 import sim as S
+    n = 4096
+    hs = HeadlessSimulation((6, 8), n_nuclei=n, seed=3)
+    T = nuclides.get_half_life(6, 8)
+    hs.time_scale = 0.9                              # slow motion: default lifetimes, particles expire
+    host = {k: np.zeros(0) for k in ("x", "y", "vx", "vy", "age", "lifetime")}
+    host["type"], host["nucleus"] = np.zeros(0, np.int32), np.zeros(0, np.int64)
+
+    def host_animate(f, n_updates, eff, st, num_steps, ts):
+        n_updates = np.broadcast_to(np.asarray(n_updates), f["x"].shape)
+        for k in range(int(n_updates.max()) if len(f["x"]) else 0):
+            x, y, age, alive = S.animate(f["type"], f["x"], f["y"], f["vx"], f["vy"], f["age"], f["lifetime"],
+                                         eff, st, ts, num_steps)
+            todo = n_updates > k
+            f["x"], f["y"], f["age"] = np.where(todo, x, f["x"]), np.where(todo, y, f["y"]), np.where(todo, age, f["age"])
+            keep = alive | ~todo
+            f = {key: v[keep] for key, v in f.items()}
+            n_updates = n_updates[keep]
+        return f
+
+    total = 0
+    for frame in range(80):
+        # make decays frequent without leaving slow motion: shorten the half-life the ensemble sees
+        # (6 % of the C-14 decay per frame, spread over the run; electrons live 20 s = ~63 frames here)
+        hs.ensemble.half_life.fill_(5.0)
+        hs.ensemble.dt_decay = -1.0                  # force set_dt_decay to recompute p for the new T
+        num_steps, eff, st, pdt = substep_plan(0.5, hs.time_scale)
+        ens = hs.ensemble
+        step0 = ens.step_index
+        # replicate update_simulation, but look at the event log before the pool drains it
+        ens.dt_phys = eff
+        ens.set_dt_decay(st)
+        ens.step(num_steps)
+        ens.resolve_overlaps()
+        ev = ens.events()
+        ev = ev[ev["ptype"] >= 0]
+        hs.substeps_used = num_steps
+        hs.pool.frame(ens, S.frame_constants(hs.time_scale, num_steps, eff, st, pdt, step0))
+        host = host_animate(host, num_steps, eff, st, num_steps, hs.time_scale)
+        if len(ev):
+            vx, vy, life = S.cosmetic_speed_lifetime_array(ev["ptype"], ev["vx"], ev["vy"], hs.time_scale,
+                                                           num_steps, pdt)
+            born = dict(x=ev["x"].astype(np.float64), y=ev["y"].astype(np.float64), vx=vx, vy=vy,
+                        age=np.zeros(len(ev)), lifetime=life, type=ev["ptype"].astype(np.int32),
+                        nucleus=ev["nucleus"].astype(np.int64))
+            remaining = np.clip(num_steps - 1 - (ev["step"].astype(np.int64) - step0), 0, num_steps)
+            born = host_animate(born, remaining, eff, st, num_steps, hs.time_scale)
+            host = {k: np.concatenate([host[k], born[k]]) for k in host}
+            total += len(ev)
+    assert total > 500 and int(hs.ensemble.event_count.item()) == 0
+    dev = hs.pool.download()
+    order = np.lexsort((host["x"], host["type"], host["nucleus"]))
+    assert len(dev) == len(order) and 0 < len(dev) < total          # some expired, some alive
+    for key in ("x", "y", "vx", "vy", "age", "lifetime"):
+        assert np.array_equal(dev[key], host[key][order]), key
+    assert np.array_equal(dev["nucleus"], host["nucleus"][order])
+    assert hs.events_dropped == 0
