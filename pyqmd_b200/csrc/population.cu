@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_pop
         if (P.uniforms) {
             if (a.ok) ua = draws.one(0, a.i, step_abs, s, 0);
             if (b.ok) ub = draws.one(0, b.i, step_abs, s, 0);
-        } else if ((a.ok && a.p >= 0.0) || (b.ok && b.p >= 0.0)) {
+        } else {
+            // unconditional (a stable nucleus simply ignores its draw): the integer work of Philox does
+            // not wait for the zn -> table-row loads and hides their latency
             draws.slot0_pair(pair, step_abs, ua, ub);
         }
         bool fa, fb;

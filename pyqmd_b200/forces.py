@@ -26,6 +26,16 @@ from .types import ParticleType
 
 logger = logging.getLogger("NuclearSim")      # same logger name as the reference (:8)
 
+_PROTON = ParticleType.PROTON.value           # 0, particles.py:6
+
+
+def _is_proton(p):
+    """The caller's particles may be the reference's own ``particles.Particle`` objects (nuclear_sim.py
+    builds the nucleus with ITS ParticleType enum when only nuclear_forces is swapped): compare the
+    enum VALUE, an ``==`` between two different Enum classes is silently False for every nucleon."""
+    t = p.type
+    return getattr(t, "value", t) == _PROTON
+
 
 class NuclearForces:
     def __init__(self):
@@ -59,7 +69,7 @@ class NuclearForces:
         h_types = np.zeros(n, dtype=np.int32)                                # :191
         for i, p in enumerate(particles):                                    # :194-199
             h_particles[i] = (p.x, p.y, p.vx, p.vy)
-            h_types[i] = 0 if p.type == ParticleType.PROTON else 1
+            h_types[i] = 0 if _is_proton(p) else 1
         center_x = sum(p.x for p in particles) / n                           # :206-207
         center_y = sum(p.y for p in particles) / n
         if n > 1024:
@@ -119,7 +129,7 @@ class NuclearForces:
         y = np.fromiter((p.y for p in particles), np.float64, n)
         vx = np.fromiter((p.vx for p in particles), np.float64, n)
         vy = np.fromiter((p.vy for p in particles), np.float64, n)
-        isp = np.fromiter((p.type == ParticleType.PROTON for p in particles), np.uint8, n)
+        isp = np.fromiter((_is_proton(p) for p in particles), np.uint8, n)
         rc = _lib.lib().pyqmd_update_particles_f64(
             x.ctypes.data, y.ctypes.data, vx.ctypes.data, vy.ctypes.data, isp.ctypes.data, n,
             self.strong_strength, self.coulomb_strength, self.pauli_strength, dt, n_steps)

@@ -213,7 +213,11 @@ def test_free_particle_pool_follows_the_host_mirror_over_frames():
     dev = hs.pool.download()
     order = np.lexsort((host["x"], host["type"], host["nucleus"]))
     assert len(dev) == len(order) and 0 < len(dev) < total          # some expired, some alive
-    for key in ("x", "y", "vx", "vy", "age", "lifetime"):
+    for key in ("age", "lifetime"):
         assert np.array_equal(dev[key], host[key][order]), key
+    # the reference squares with ``**`` (libm pow, < 1 ulp but not correctly rounded), the device with a
+    # product: |v| may differ in the last bit, and with it the renormalised velocity
+    for key in ("x", "y", "vx", "vy"):
+        assert np.allclose(dev[key], host[key][order], rtol=1e-15, atol=0), key
     assert np.array_equal(dev["nucleus"], host["nucleus"][order])
     assert hs.events_dropped == 0

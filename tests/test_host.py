@@ -209,3 +209,22 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "SO_PATH", "/nonexistent/libpyqmd_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_dropin_recognises_protons_of_a_foreign_particle_class():
+    """nuclear_sim.py keeps building particles with the reference's own ParticleType when only
+    nuclear_forces is swapped: the drop-in must read the enum VALUE (0 = proton, particles.py:6)."""
+    import enum
+
+    from pyqmd_b200 import forces
+
+    class ForeignType(enum.Enum):
+        PROTON = 0
+        NEUTRON = 1
+
+    class P:
+        def __init__(self, t):
+            self.type = t
+    assert forces._is_proton(P(ForeignType.PROTON)) and not forces._is_proton(P(ForeignType.NEUTRON))
+    assert forces._is_proton(P(forces.ParticleType.PROTON)) and not forces._is_proton(P(forces.ParticleType.NEUTRON))
+    assert forces._is_proton(P(0)) and not forces._is_proton(P(1))
