@@ -179,7 +179,8 @@ enum { PYQMD_HL_INF = 0, PYQMD_HL_TABLE = 1, PYQMD_HL_BAND = 2 };
 typedef struct {
     double half_life;   /* PYQMD_HL_TABLE: database value, seconds (may be +inf)  :257-262 */
     double p_decay;     /* probability per sub-step for this run's dt_decay, computed on the
-                           host exactly as particles.py:134-144; < 0 = stable (no draw) */
+                           host exactly as particles.py:134-144; < 0 = stable (no draw); NaN for
+                           PYQMD_HL_BAND rows (the value is per nucleus, not per nuclide) */
     double band_a, band_b, band_unit; /* PYQMD_HL_BAND: 10**uniform(a,b)*unit     :311-328 */
     double opt_cum[2];  /* running sums of the branch probabilities               :222-227 */
     int32_t opt_zn[2];  /* daughter (Z << 16) | N                                             */

@@ -5,29 +5,28 @@
 // (OtsoBear/PyQMD decay_chains.py:400-421, same code as particles.py:126-147) followed, on a
 // hit, by the (Z, N) / half-life part of handle_decay (nuclear_sim.py:213,288-289,353).
 //
-// One thread owns TWO neighbouring nuclei (global ids 2k, 2k+1) for all n_steps sub-steps of a
-// launch: one Philox4x32-10 call yields both every-step draws (DrawSource, slot 0), which halves the
-// integer work that bounded the round-1 kernel (ncu r01h: ALU 41 %, issue 66 %, HBM 32 %).  State is
+// One thread owns FOUR neighbouring nuclei (global ids 4k .. 4k+3) for all n_steps sub-steps of a
+// launch: a Philox4x32-10 call yields the every-step draws of two nuclei (DrawSource, slot 0), which
+// halves the integer work that bounded the round-1 kernel (ncu r01h: ALU 41 %, issue 66 %, HBM 32 %),
+// and the two independent calls plus one 16-byte load of the four (Z, N) words give the scheduler
+// something to overlap with the dependent table-row loads.  State is
 // kept in registers; HBM traffic per nucleus-launch is the 4-byte (Z, N) word: half-life and per-step
 // probability of a tabulated nuclide come from its (L2/L1-resident) table row, the per-nucleus side
 // arrays are read only for nuclides with an ESTIMATED half-life (10**uniform(a, b), one value per
 // nucleus) or when the caller supplied its own per-nucleus values (PYQMD_POP_PER_NUCLEUS_STATE), and
 // written only for nuclei that decayed.  Draws: Philox keyed by (seed; global id, step, slot) or, for
-// the bit-exact parity path, a caller-supplied array.  Per-step decay counts are reduced
-// block-wide -> one atomicAdd per block and column.
+// the bit-exact parity path, a caller-supplied array.  Per-step decay counts: shared-memory atomics
+// into a block-local table, flushed once per launch.
 #include "common.cuh"
 #include "decay_device.cuh"
 
 namespace pyqmd {
 
+#ifndef PYQMD_POP_MINBLOCKS
+#define PYQMD_POP_MINBLOCKS 2
+#endif
 constexpr int kPopThreads = 256;
-
-struct PopNucleus {
-    int i;            // local index, valid when ok (populations are < 2^31 nuclei per GPU)
-    bool ok, dirty;
-    int32_t zn;
-    double T, p;      // T is only defined after a decay in this launch (it is never read before)
-};
+constexpr int kNPT = 4;           // nuclei per thread: global ids 4k .. 4k+3, two Philox calls
 
 // table row of an in-range (Z, N): callers validate on the host, daughters come from the table
 __device__ __forceinline__ const pyqmd_nuclide_entry* row_of(const pyqmd_nuclide_entry* table, int32_t zn)
@@ -35,103 +34,149 @@ __device__ __forceinline__ const pyqmd_nuclide_entry* row_of(const pyqmd_nuclide
     return table + ((zn >> 16) * PYQMD_TABLE_NDIM + (zn & 0xffff));
 }
 
-__device__ __forceinline__ void pop_load(const pyqmd_population& P, PopNucleus& a)
-{
-    a.dirty = false;
-    a.zn = 0; a.T = 0.0; a.p = -1.0;
-    if (!a.ok) return;
-    a.zn = P.zn[a.i];
-    const pyqmd_nuclide_entry* row = row_of(P.table, a.zn);
-    if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || row->kind == PYQMD_HL_BAND)
-        a.p = P.p_decay[a.i];
-    else
-        a.p = row->p_decay;
-}
+struct DecayOut {
+    double p;
+    int32_t zn;
+    int mode, watch;
+};
 
-// should_decay with the draw u0 (decay_chains.py:400-421) and, on a hit, the (Z, N) / half-life part
-// of handle_decay (nuclear_sim.py:213,288-289,353).  Returns the decay mode that was counted, or NONE.
-__device__ __forceinline__ int pop_step(const pyqmd_population& P, const DrawSource& draws, PopNucleus& a,
-                                        double u0, uint32_t step_abs, int s, bool& fired, int& watch)
+// The (Z, N) / half-life part of handle_decay (nuclear_sim.py:213,288-289,353) for a nucleus whose
+// should_decay fired; writes the new state back at once.  Rare and heavy (float64 pow for estimated
+// half-lives): out of line and by value, so that the every-step path keeps its state in few registers.
+__device__ __noinline__ DecayOut pop_decay(const pyqmd_population& P, const DrawSource draws, int i,
+                                           int32_t zn, double p, uint32_t step_abs, int s)
 {
-    fired = false;
-    watch = -1;
-    if (!a.ok || !(a.p >= 0.0)) return PYQMD_DECAY_NONE;    // stable: no draw, decay_chains.py:403
-    fired = u0 < a.p;                                       // :421
-    if (!fired) return PYQMD_DECAY_NONE;
-    const uint64_t gid = (uint64_t)(P.id_base + a.i);
-    const pyqmd_nuclide_entry* cur = row_of(P.table, a.zn);
+    DecayOut o;
+    o.p = p; o.zn = zn; o.mode = PYQMD_DECAY_NONE; o.watch = -1;
+    const uint64_t gid = (uint64_t)(P.id_base + i);
+    const pyqmd_nuclide_entry* cur = row_of(P.table, zn);
     int k = 0;
-    if (cur->n_opt > 1) k = pick_option(cur, draws.one(gid, a.i, step_abs, s, 1));   // :218-229
+    if (cur->n_opt > 1) k = pick_option(cur, draws.one(gid, i, step_abs, s, 1));     // :218-229
     const int mode = cur->opt_mode[k];
-    if (mode == PYQMD_DECAY_NONE) return mode;              // :231-232
+    if (mode == PYQMD_DECAY_NONE) return o;                 // :231-232
     for (int wch = 0; wch < P.n_watch; ++wch)
-        if (P.watch_zn[wch] == a.zn) watch = wch;
-    a.dirty = true;
-    a.zn = cur->opt_zn[k];                                  // nuclear_sim.py:288-289
-    const pyqmd_nuclide_entry* nxt = lookup(P.table, a.zn);
-    const double u3 = (nxt->kind == PYQMD_HL_BAND) ? draws.one(gid, a.i, step_abs, s, 3) : 0.0;
+        if (P.watch_zn[wch] == zn) o.watch = wch;
+    o.mode = mode;
+    o.zn = cur->opt_zn[k];                                  // nuclear_sim.py:288-289
+    const pyqmd_nuclide_entry* nxt = lookup(P.table, o.zn);
+    const double u3 = (nxt->kind == PYQMD_HL_BAND) ? draws.one(gid, i, step_abs, s, 3) : 0.0;
     bool used3;
-    daughter_half_life(nxt, u3, P.dt_decay, a.T, a.p, used3);                        // nuclear_sim.py:353
-    return mode;
+    double T;
+    daughter_half_life(nxt, u3, P.dt_decay, T, o.p, used3); // nuclear_sim.py:353
+    P.zn[i] = o.zn;
+    P.half_life[i] = T;
+    P.p_decay[i] = o.p;
+    return o;
 }
 
-__global__ void __launch_bounds__(kPopThreads) population_kernel(const pyqmd_population P,
-                                                                 const int n_steps)
-{
-    __shared__ unsigned int scount[PYQMD_COUNT_COLS];
-    // global pair index: both nuclei of a pair share one Philox counter, whatever the sharding
-    const int j = (int)(blockIdx.x * kPopThreads + threadIdx.x);
-    const uint64_t pair = (uint64_t)(P.id_base >> 1) + (uint64_t)j;
-    const int n = (int)P.n;
-    PopNucleus a, b;
-    a.i = 2 * j - (int)(P.id_base & 1);
-    b.i = a.i + 1;
-    a.ok = a.i >= 0 && a.i < n;
-    b.ok = b.i < n;
-    pop_load(P, a);
-    pop_load(P, b);
-    const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
+constexpr int kSmemSteps = 64;    // sub-steps per launch whose counters fit the block-local table
 
-    for (int s = 0; s < n_steps; ++s) {
-        const uint32_t step_abs = P.step0 + (uint32_t)s;
-        double ua = 0.0, ub = 0.0;
-        if (P.uniforms) {
-            if (a.ok) ua = draws.one(0, a.i, step_abs, s, 0);
-            if (b.ok) ub = draws.one(0, b.i, step_abs, s, 0);
-        } else {
-            // unconditional (a stable nucleus simply ignores its draw): the integer work of Philox does
-            // not wait for the zn -> table-row loads and hides their latency
-            draws.slot0_pair(pair, step_abs, ua, ub);
-        }
-        bool fa, fb;
-        int wa, wb;
-        const int ma = pop_step(P, draws, a, ua, step_abs, s, fa, wa);
-        const int mb = pop_step(P, draws, b, ub, step_abs, s, fb, wb);
-        if (P.decided) {
-            if (a.ok) P.decided[(int64_t)s * n + a.i] = fa ? 1 : 0;
-            if (b.ok) P.decided[(int64_t)s * n + b.i] = fb ? 1 : 0;
-        }
-        // block-aggregated counters; one barrier per sub-step when nothing in the block decayed
-        const bool counted = ma != PYQMD_DECAY_NONE || mb != PYQMD_DECAY_NONE;
-        if (__syncthreads_or(counted)) {
-            if (threadIdx.x < PYQMD_COUNT_COLS) scount[threadIdx.x] = 0;
-            __syncthreads();
-            if (ma != PYQMD_DECAY_NONE) {
-                atomicAdd(&scount[ma], 1u);
-                if (wa >= 0) atomicAdd(&scount[8 + wa], 1u);
-            }
-            if (mb != PYQMD_DECAY_NONE) {
-                atomicAdd(&scount[mb], 1u);
-                if (wb >= 0) atomicAdd(&scount[8 + wb], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x < PYQMD_COUNT_COLS && scount[threadIdx.x] && P.step_counts)
-                atomicAdd(P.step_counts + (int64_t)s * PYQMD_COUNT_COLS + threadIdx.x,
-                          (unsigned long long)scount[threadIdx.x]);
+struct Quad {
+    int32_t zn[kNPT];
+    bool ok[kNPT];
+};
+
+__device__ __forceinline__ Quad load_quad(const pyqmd_population& P, int64_t q, int n, bool aligned)
+{
+    Quad r;
+    const int64_t i0 = kNPT * q - (P.id_base & 3);
+    if (aligned && i0 + kNPT <= n) {                        // one 16-byte load
+        const int4 v = *reinterpret_cast<const int4*>(P.zn + i0);
+        r.zn[0] = v.x; r.zn[1] = v.y; r.zn[2] = v.z; r.zn[3] = v.w;
+#pragma unroll
+        for (int k = 0; k < kNPT; ++k) r.ok[k] = true;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kNPT; ++k) {
+            r.ok[k] = i0 + k >= 0 && i0 + k < n;
+            r.zn[k] = r.ok[k] ? P.zn[i0 + k] : 0;
         }
     }
-    if (a.ok && a.dirty) { P.zn[a.i] = a.zn; P.half_life[a.i] = a.T; P.p_decay[a.i] = a.p; }
-    if (b.ok && b.dirty) { P.zn[b.i] = b.zn; P.half_life[b.i] = b.T; P.p_decay[b.i] = b.p; }
+    return r;
+}
+
+// Persistent grid (a few blocks per SM), grid-stride over quads, the next quad's (Z, N) words
+// prefetched while the current one is processed: the kernel no longer pays one DRAM round trip plus
+// one block launch per 256 threads of useful work (ncu r02b: 32 % of the stall samples sat on the
+// first load, 9 % on the per-step barrier).  Decay counts go to a block-local table with shared-memory
+// atomics and are flushed once at the end.
+__global__ void __launch_bounds__(kPopThreads, PYQMD_POP_MINBLOCKS) population_kernel(const pyqmd_population P,
+                                                                    const int n_steps, const int64_t n_quads)
+{
+    __shared__ unsigned int scount[kSmemSteps][PYQMD_COUNT_COLS];
+    const bool local_counts = n_steps <= kSmemSteps;
+    if (local_counts) {
+        for (int k = threadIdx.x; k < n_steps * PYQMD_COUNT_COLS; k += kPopThreads)
+            (&scount[0][0])[k] = 0;
+        __syncthreads();
+    }
+    const int n = (int)P.n;
+    const bool aligned = (P.id_base & 3) == 0;
+    const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
+    const int64_t stride = (int64_t)gridDim.x * kPopThreads;
+    int64_t q = (int64_t)blockIdx.x * kPopThreads + threadIdx.x;
+    Quad cur;
+    if (q < n_quads) cur = load_quad(P, q, n, aligned);
+    for (; q < n_quads; q += stride) {
+        const Quad me = cur;
+        // prefetch: the next quad's words travel from DRAM while this one is processed (a second stage
+        // for the dependent table-row loads was measured and did not pay: 2.19e11 vs 2.37e11 steps/s)
+        if (q + stride < n_quads) cur = load_quad(P, q + stride, n, aligned);
+        const int i0 = (int)(kNPT * q - (P.id_base & 3));   // local index of the quad's first nucleus
+        const uint64_t quad = (uint64_t)(P.id_base >> 2) + (uint64_t)q;              // global quad id
+        int32_t zn[kNPT];
+        double p[kNPT];
+        // per-step probability: the table row's, unless the half-life is a per-nucleus estimate (the
+        // row then holds NaN) or the caller supplied its own per-nucleus values
+#pragma unroll
+        for (int k = 0; k < kNPT; ++k) {
+            zn[k] = me.zn[k];
+            p[k] = -1.0;
+            if (me.ok[k]) {
+                p[k] = row_of(P.table, zn[k])->p_decay;
+                if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || p[k] != p[k]) p[k] = P.p_decay[i0 + k];
+            }
+        }
+        for (int s = 0; s < n_steps; ++s) {
+            const uint32_t step_abs = P.step0 + (uint32_t)s;
+            double u[kNPT];
+            if (P.uniforms) {
+#pragma unroll
+                for (int k = 0; k < kNPT; ++k) u[k] = me.ok[k] ? draws.one(0, i0 + k, step_abs, s, 0) : 1.0;
+            } else {
+                // unconditional (a stable nucleus ignores its draw): Philox does not wait for the loads
+                draws.slot0_pair(2 * quad, step_abs, u[0], u[1]);
+                draws.slot0_pair(2 * quad + 1, step_abs, u[2], u[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < kNPT; ++k) {
+                // stable (p < 0): no draw, decay_chains.py:403; otherwise random() < p, :421
+                const bool fired = me.ok[k] && p[k] >= 0.0 && u[k] < p[k];
+                if (P.decided && me.ok[k]) P.decided[(int64_t)s * n + i0 + k] = fired ? 1 : 0;
+                if (fired) {
+                    const DecayOut o = pop_decay(P, draws, i0 + k, zn[k], p[k], step_abs, s);
+                    zn[k] = o.zn; p[k] = o.p;
+                    if (o.mode != PYQMD_DECAY_NONE && P.step_counts) {
+                        if (local_counts) {
+                            atomicAdd(&scount[s][o.mode], 1u);
+                            if (o.watch >= 0) atomicAdd(&scount[s][8 + o.watch], 1u);
+                        } else {
+                            unsigned long long* row = P.step_counts + (int64_t)s * PYQMD_COUNT_COLS;
+                            atomicAdd(row + o.mode, 1ULL);
+                            if (o.watch >= 0) atomicAdd(row + 8 + o.watch, 1ULL);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (local_counts && P.step_counts) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_steps * PYQMD_COUNT_COLS; k += kPopThreads) {
+            const unsigned int c = (&scount[0][0])[k];
+            if (c) atomicAdd(P.step_counts + k, (unsigned long long)c);
+        }
+    }
 }
 
 }  // namespace pyqmd
@@ -143,14 +188,18 @@ extern "C" int pyqmd_population_step(const pyqmd_population* p, int32_t n_steps,
     PYQMD_REQUIRE(p != nullptr, "population descriptor is NULL");
     PYQMD_REQUIRE(n_steps >= 0 && p->n >= 0 && p->id_base >= 0, "n_steps, n, id_base >= 0");
     PYQMD_REQUIRE(p->n < 2147483647LL / 2, "at most 2^30 nuclei per launch");
+    PYQMD_REQUIRE((reinterpret_cast<uintptr_t>(p->zn) & 15) == 0, "zn must be 16-byte aligned");
     if (p->n == 0 || n_steps == 0) return PYQMD_OK;
     PYQMD_REQUIRE(p->zn && p->half_life && p->p_decay && p->table, "state arrays / table");
     PYQMD_REQUIRE(p->n_watch >= 0 && p->n_watch <= 8, "n_watch in [0, 8]");
-    // pairs of global ids covered by [id_base, id_base + n): one thread each
-    const int64_t n_pairs = ((p->id_base + p->n + 1) >> 1) - (p->id_base >> 1);
-    const int64_t blocks = (n_pairs + kPopThreads - 1) / kPopThreads;
-    PYQMD_REQUIRE(blocks <= 2147483647LL, "population too large for one launch");
-    population_kernel<<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps);
+    // quads of global ids covered by [id_base, id_base + n): grid-stride over them
+    const int64_t n_quads = ((p->id_base + p->n + 3) >> 2) - (p->id_base >> 2);
+    int dev = 0, sms = 0;
+    PYQMD_CUDA_CHECK(cudaGetDevice(&dev));
+    PYQMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t blocks = (n_quads + kPopThreads - 1) / kPopThreads;
+    if (blocks > (int64_t)sms * PYQMD_POP_MINBLOCKS) blocks = (int64_t)sms * PYQMD_POP_MINBLOCKS;   // persistent grid
+    population_kernel<<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps, n_quads);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }
