@@ -534,6 +534,18 @@ def bench_cloud(ctx, workload, K, W, with_e2e=True):
                                     "TFLOP/s); nominal %.1f" % ctx.peak_info},
         "clocks": clocks, "gpu_launches": K * 4,
     }
+    if ctx.world > 1 and sym:
+        # where the rest of the scaling goes: this rank's share of the pair forces, timed alone
+        cloud.profile = []
+        ctx.timed(lambda: cloud.step(1), 3, 0, clocks=False)
+        mine_ms = torch.tensor([cloud.pair_kernel_ms()], device=ctx.dev, dtype=torch.float64)
+        cloud.profile = None
+        allms = [torch.zeros_like(mine_ms) for _ in range(ctx.world)]
+        ctx.dist.all_gather(allms, mine_ms)
+        per_rank = [float(t.item()) for t in allms]
+        res["details"]["pair_kernel_ms_per_rank"] = per_rank
+        res["details"]["pair_kernel_imbalance"] = max(per_rank) / (sum(per_rank) / len(per_rank)) - 1.0
+        res["details"]["step_ms_outside_pair_kernel"] = sec / K * 1e3 - max(per_rank)
     if with_e2e:
         k2, w2 = max(3, K // 2), 2
         if ctx.world == 1:

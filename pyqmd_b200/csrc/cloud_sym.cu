@@ -428,10 +428,12 @@ extern "C" int pyqmd_cloud_pair_forces(const float* pos, const uint8_t* is_proto
     sp.n_parts = n_parts;
     sp.far_enabled = (strong > 0.f && !L.far_needs_clamp) ? 1 : 0;
     sp.scale = ldexpf(1.0f, scale_log2_for(n));
-    // ~24 units per resident-block slot of this part (148 SMs x 2), 4..64 tiles each (a sweep of
-    // 8..128 tiles per unit on B200 at N = 1M changed the step time by < 0.8 %)
+    // ~96 units per resident-block slot of this part (148 SMs x 2), 4..64 tiles each: the hardware
+    // hands blocks to SMs as slots free up, so the idle tail of a launch is about half a unit -- 0.5 %
+    // of the step at ~100 units per slot whatever the number of parts (round 1 used 24 per slot: 2 % at
+    // 8 GPUs).  A sweep of 8..128 tiles per unit on B200 at N = 1M changed the step time by < 0.8 %.
     const double tiles_total = 0.5 * (double)sp.nb * (double)nt / n_parts;
-    int tpu = (int)(tiles_total / (296.0 * 24.0));
+    int tpu = (int)(tiles_total / (296.0 * 96.0));
     if (tpu > 64) tpu = 64;
     if (tpu < 4) tpu = 4;
     sp.tiles_per_unit = tpu;

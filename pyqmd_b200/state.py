@@ -510,6 +510,13 @@ class NucleonCloud:
                                  if self.world > 1 else self.acc)
         self.force_scale_log2 = int(_lib.lib().pyqmd_cloud_force_scale_log2(max(self.n, 1)))
         self.steps_done = 0
+        self.profile = None              # set to [] to collect (start, end) events of the pair-force launches
+
+    def pair_kernel_ms(self):
+        """Mean device time of this rank's pair-force launches collected in ``self.profile``."""
+        torch.cuda.synchronize(self.device)
+        t = [a.elapsed_time(b) for a, b in self.profile]
+        return sum(t) / max(len(t), 1)
 
     def _setup_peer_buffers(self, padded):
         """acc + both position replicas in symmetric memory; device arrays of the peers' pointers."""
@@ -557,11 +564,16 @@ class NucleonCloud:
                     _lib.ptr(self.force), self.is_proton.data_ptr(), self.n, self.i0, self.i1, S, Cc,
                     P, self.dt, self.workspace.data_ptr(), stream), "pyqmd_cloud_step")
             else:
-                import torch.distributed as dist
+                if self.profile is not None:     # per-rank kernel time (load-balance evidence)
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 _lib.check(lib.pyqmd_cloud_pair_forces(
                     self.pos.data_ptr(), self.is_proton.data_ptr(), self.n, self.rank, self.world,
                     S, Cc, P, self.acc.data_ptr(), self.workspace.data_ptr(), stream),
                     "pyqmd_cloud_pair_forces")
+                if self.profile is not None:
+                    ev[1].record()
+                    self.profile.append(ev)
                 if self._symm is not None:
                     # peer-memory exchange fused with the integration (no NCCL on the data path)
                     hdl = self._symm["hdl"]["acc"]

@@ -9,14 +9,14 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np
 import torch
 
-from gpu_util import extent_of, oracle_step
+from gpu_util import extent_of, force_error, oracle_step
 from pyqmd_b200.state import NucleusEnsemble
 
 
 
 def run(seed=0, trials=40):
   rng = np.random.default_rng(seed)
-  worst, n_cases, n_amb, detail = 0.0, 0, 0, None
+  worst, worst_f, n_cases, n_amb, detail = 0.0, 0.0, 0, 0, None
   for trial in range(trials):
       S, Cq, P = float(rng.uniform(0, 400)), float(rng.uniform(0, 80)), float(rng.uniform(0, 80))
       dt = float(rng.choice([1 / 240, 1 / 60, 1e-3]))
@@ -34,12 +34,15 @@ def run(seed=0, trials=40):
           off.append(o); cnt.append(a); zn.append((int(t.sum()) << 16) | int(a - t.sum())); o += a
       ens = NucleusEnsemble(np.array(zn, np.int32), np.array(off, np.int64), np.array(cnt, np.int32),
                             np.concatenate(pos), np.concatenate(vel), np.concatenate(isp), decay=False,
-                            dt_phys=dt, strengths=(S, Cq, P))
+                            dt_phys=dt, strengths=(S, Cq, P), keep_force=True)
       ens.step(1)
       got = ens.pos.cpu().numpy()
+      gotf = ens.force.cpu().numpy()
       for k, a in enumerate(sizes):
-          ox, oy, _, _, _, _, amb = oracle_step(pos[k], vel[k], isp[k], dt, S, Cq, P)
+          ox, oy, _, _, fx, fy, amb = oracle_step(pos[k], vel[k], isp[k], dt, S, Cq, P)
           ok = ~amb
+          if ok.any() and np.hypot(fx[ok], fy[ok]).max() > 1e-3:
+              worst_f = max(worst_f, force_error(gotf[off[k]:off[k] + a], fx, fy, amb))
           n_amb += int(amb.sum())
           if ok.any():
               ext = max(extent_of(pos[k]), 1.0)      # A = 1 has no extent: absolute FP32 rounding then
@@ -56,10 +59,12 @@ def run(seed=0, trials=40):
                                 is_proton=int(isp[k][i]))
               worst = max(worst, err)
           n_cases += 1
-  return {"nuclei": n_cases, "worst_pos_err": worst, "ambiguous_nucleons": n_amb, "worst_case": detail}
+  return {"nuclei": n_cases, "worst_pos_err": worst, "worst_force_err_l2": worst_f, "ambiguous_nucleons": n_amb,
+          "worst_case": detail}
 
 
 if __name__ == "__main__":
     res = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
     print(json.dumps(res))
     assert res["worst_pos_err"] <= 1e-5, res["worst_pos_err"]
+    assert res["worst_force_err_l2"] <= 1e-5, res["worst_force_err_l2"]

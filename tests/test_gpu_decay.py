@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import unhex
-from gpu_util import POS_TOL, oracle_step, pos_error
+from gpu_util import FORCE_TOL, POS_TOL, force_error, oracle_step, pos_error
 from oracle import decay_oracle as dor
 from oracle import oracle as orc
 
@@ -277,7 +277,7 @@ def test_full_size_mixed_ensemble_1M_properties():
     n = 1_000_000
     T_c14 = dor.half_life(*C14)[0]
     ens = NucleusEnsemble.from_templates(README_ISOTOPES, n, dt_decay=T_c14 * 2e-3, seed=77,
-                                         event_capacity=1 << 16)
+                                         event_capacity=1 << 16, keep_force=True)
     assert ens.pairs_per_step() == sum((z + m) * (z + m - 1) for z, m in README_ISOTOPES) * (n // 9) + \
         sum((z + m) * (z + m - 1) for z, m in README_ISOTOPES[: n % 9])
     off, cnt0 = ens.offsets.cpu().numpy(), ens.count.cpu().numpy().copy()
@@ -291,9 +291,12 @@ def test_full_size_mixed_ensemble_1M_properties():
         if zn1[k] != zn0[k]:
             continue                                        # decayed in this sub-step: covered elsewhere
         p0, isp = before[k]
-        ox, oy, _, _, _, _, amb = oracle_step(p0, np.zeros_like(p0), isp, ens.dt_phys)
+        ox, oy, _, _, fx, fy, amb = oracle_step(p0, np.zeros_like(p0), isp, ens.dt_phys)
         got = ens.pos[off[k]:off[k] + cnt0[k]].cpu().numpy()
         assert pos_error(p0, got, ox, oy, amb) <= POS_TOL, k
+        if cnt0[k] > 1:
+            f_dev = ens.force[off[k]:off[k] + cnt0[k]].cpu().numpy()
+            assert force_error(f_dev, fx, fy, amb) <= FORCE_TOL, k
     ens.step(4)
     assert torch.isfinite(ens.pos).all()
     events = int(ens.event_count.item())

@@ -14,7 +14,8 @@ import pytest
 import torch
 
 from conftest import ROOT, unhex
-from gpu_util import (AMB_TOL, FORCE_TOL, POS_TOL, extent_of, force_error, oracle_step, pos_error,
+from gpu_util import (AMB_TOL, FORCE_TOL, POS_TOL, admissible_force_check, extent_of, force_error, oracle_step,
+                      pos_error,
                       single_nucleus_ensemble)
 from oracle import oracle as orc
 
@@ -87,8 +88,8 @@ def test_u238_teacher_forced_1000_steps(u238_traj):
     pos = (st0[:, :2] - origin).astype(np.float32)
     vel = st0[:, 2:].astype(np.float32)
     ens = single_nucleus_ensemble(pos, vel, isp, dt_phys=dt)
-    worst_pos = worst_f = 0.0
-    amb_total = 0
+    worst_pos = worst_f = amb_worst = 0.0
+    amb_total = amb_checked = 0
     for s in range(1000):
         p0 = ens.pos.cpu().numpy().copy()
         v0 = ens.vel.cpu().numpy().copy()
@@ -102,11 +103,19 @@ def test_u238_teacher_forced_1000_steps(u238_traj):
         amb_total += int(amb.sum())
         assert e_pos <= POS_TOL, (s, e_pos)
         assert e_f <= FORCE_TOL, (s, e_f)
+        if amb.any():
+            # excluded from the norms above, but not unchecked: the device took one of the two branches
+            c, w = admissible_force_check(p0, isp, f1, fx, fy, amb)
+            amb_checked += c
+            amb_worst = max(amb_worst, w)
+            assert w <= 1e-4, (s, w)
+    assert amb_checked > 0.5 * amb_total
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "c1_parity.json"), "w") as f:
         json.dump(dict(config="C1 U-238 teacher-forced", steps=1000, worst_pos_err=worst_pos,
                        worst_force_err_l2=worst_f, ambiguous_nucleon_steps=amb_total,
-                       tolerance=POS_TOL), f)
+                       ambiguous_checked_against_branch_alternatives=amb_checked,
+                       ambiguous_worst_mismatch=amb_worst, tolerance=POS_TOL), f)
 
 
 def test_u238_free_running_drift_report(u238_traj):
@@ -216,7 +225,7 @@ def test_full_size_ensemble_properties():
     rotated replicas."""
     from pyqmd_b200.state import NucleusEnsemble
     n_nuc = 65536
-    ens = NucleusEnsemble.from_templates(((82, 126),), n_nuc, decay=False)
+    ens = NucleusEnsemble.from_templates(((82, 126),), n_nuc, decay=False, keep_force=True)
     assert ens.pairs_per_step() == n_nuc * 208 * 207
     p0 = ens.pos.clone()
     ens.step(1)
@@ -235,10 +244,12 @@ def test_full_size_ensemble_properties():
     rng = np.random.default_rng(0)
     p0h, p1h = p0.view(n_nuc, 208, 2).cpu().numpy(), pos.cpu().numpy()
     isp = ens.is_proton.view(n_nuc, 208).cpu().numpy()
+    fh = ens.force.view(n_nuc, 208, 2).cpu().numpy()
     for k in rng.integers(0, n_nuc, 48):
-        ox, oy, _, _, _, _, amb = oracle_step(p0h[k], np.zeros((208, 2), np.float32), isp[k],
-                                              ens.dt_phys)
+        ox, oy, _, _, fx, fy, amb = oracle_step(p0h[k], np.zeros((208, 2), np.float32), isp[k],
+                                                ens.dt_phys)
         assert pos_error(p0h[k], p1h[k], ox, oy, amb) <= POS_TOL
+        assert force_error(fh[k], fx, fy, amb) <= FORCE_TOL      # one step moves a nucleon by 1.5e-5 F only
 
 
 def test_branch_census_matches_oracle_statistics():
@@ -333,7 +344,10 @@ def test_single_system_sizes_through_the_host_api(n):
     x, y = x32.astype(np.float64), y32.astype(np.float64)
     vx, vy = np.zeros(n), np.zeros(n)
     p0 = np.stack([x32, y32], 1)
-    ox, oy, _, _, _, _, amb = oracle_step(p0, np.zeros_like(p0), isp, 1 / 240)
+    ox, oy, _, _, fx, fy, amb = oracle_step(p0, np.zeros_like(p0), isp, 1 / 240)
     NuclearForces().step_arrays(x, y, vx, vy, isp, 1 / 240)
     got = np.stack([x, y], 1).astype(np.float32)
     assert pos_error(p0, got, ox, oy, amb) <= POS_TOL
+    # force gate: from rest v' = 0.85 F dt (nuclear_forces.py:312-319), so F is read off the velocity
+    f_dev = np.stack([vx, vy], 1) / (0.85 / 240)
+    assert force_error(f_dev, fx, fy, amb) <= FORCE_TOL

@@ -16,3 +16,4 @@ def test_random_nuclei_against_oracle(seed):
     res = fuzz_forces.run(seed, trials=10)
     assert res["nuclei"] == 480
     assert res["worst_pos_err"] <= 1e-5, res
+    assert res["worst_force_err_l2"] <= 1e-5, res
