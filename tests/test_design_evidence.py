@@ -7,6 +7,13 @@ tile).  This test measures on settled Pb-208 nuclei (reference layout, 12 app fr
 4 sub-steps + resolve_overlaps) how often such a vote would pass with the ring kernel's granularity
 (4 nucleons per lane, rings of 26 lanes, 2 warps), for Morton-ordered nucleons and for the reference's
 list order (shell by shell, which is what the kernels sweep today).
+
+Outcome on the B200 (round 2, profiles/raw_r02/far_vote_ab.log): with the vote in both ensemble kernels
+(per packed call, `__all_sync` on d2 >= 81, far law = 2 MUFU + 9 FMA-pipe ops) every workload lost 15-23 %
+-- Pb-208 free-running 1.147e12 -> 0.973e12 pairs/s, U-238 1.206e12 -> 0.930e12 -- because a branch
+per call stops the compiler from interleaving the eight independent evaluations of a ring step, which is
+what hides the MUFU latency; and settled, Morton-ordered nuclei (39 % of the calls all-far, below) were
+no faster than list-ordered ones (0.971e12 vs 0.974e12).  Not shipped; the numbers stay here.
 """
 import numpy as np
 
