@@ -3,8 +3,13 @@
  * damped Euler integrate -> per-nucleus stochastic decay) on NVIDIA B200 (sm_100a).
  *
  * Plain pointers and sizes only; no torch / C++ types.  All device pointers are caller
- * owned (e.g. torch tensors).  Every call is stream-ordered and non-blocking unless it is a
- * *_host entry point.  Return value: 0 on success, negative PYQMD_ERR_* otherwise (no
+ * owned (e.g. torch tensors).  Entry points that take DEVICE pointers are stream-ordered and
+ * non-blocking.  Of the entry points that take HOST arrays, section (A) --
+ * pyqmd_update_forces_and_positions, pyqmd_update_particles_f64, pyqmd_cloud_step_host -- BLOCKS until
+ * the result is back in the caller's arrays (like the reference's event.wait() + .get(),
+ * nuclear_forces.py:221,227), while pyqmd_ensemble_step_host only ENQUEUES its chunked copies and
+ * kernels and joins them into `stream`: its host arrays are valid after that stream has been
+ * synchronised.  Return value: 0 on success, negative PYQMD_ERR_* otherwise (no
  * exceptions cross the ABI); pyqmd_last_error() gives the message for the calling thread.
  *
  * Each entry point names the reference interface it replaces (file:line relative to the

@@ -61,3 +61,12 @@ def decay_events():
 @pytest.fixture(scope="session")
 def u238_traj():
     return dict(np.load(os.path.join(GOLD, "u238_traj.npz")))
+
+
+@pytest.fixture(params=["ring", "block"])
+def ensemble_kernel(request, monkeypatch):
+    """Pins pyqmd_ensemble_step's choice between the warp-local ring kernel and the block-wide ring
+    (csrc/ensemble.cu) so that BOTH see the parity case, whatever the automatic dispatch would pick for
+    its size (small test ensembles would otherwise always take the low-latency block ring)."""
+    monkeypatch.setenv("PYQMD_ENSEMBLE_KERNEL", request.param)
+    return request.param

@@ -142,7 +142,7 @@ def _device_nucleus(rec, dt_decay, **kw):
                            p_decay=np.array([nuclides.decay_probability(T, dt_decay)]), **kw)
 
 
-def test_substep_loops_against_reference_goldens(decay_events):
+def test_substep_loops_against_reference_goldens(decay_events, ensemble_kernel):
     """decay test -> handle_decay slice -> force step (nuclear_sim.py:165-173) on the device with
     the golden draws: Z, N, nucleon types/count and decisions exact; half-life exact when it
     comes from the table; positions within the per-step tolerance."""
@@ -194,7 +194,7 @@ def test_substep_loops_against_reference_goldens(decay_events):
         assert len(ev) == n_dec
 
 
-def test_chain_walk_events_on_device(decay_events):
+def test_chain_walk_events_on_device(decay_events, ensemble_kernel):
     """Forced decays (p = 1) down the golden chains: daughters, particle bookkeeping and the
     emitted particle (type, direction, speed) against the reference's records."""
     for walk in decay_events["walks"]:
@@ -355,7 +355,7 @@ def test_random_nuclides_walk_the_same_chains_as_the_oracle():
     assert (modes[[1, 2, 3]] > 100).all() and modes[5] + modes[6] > 0     # alpha, beta-, beta+, n / p emission
 
 
-def test_random_ensemble_decay_and_force_steps_teacher_forced():
+def test_random_ensemble_decay_and_force_steps_teacher_forced(ensemble_kernel):
     """Randomised differential test of the fused ensemble sub-step (decay test -> transmutation with
     list compaction / type flips -> force -> integrate): 150 random nuclei (2..240 nucleons, random
     Z/N, frequent decays), every sub-step compared with OracleNucleus.substep from the device's own

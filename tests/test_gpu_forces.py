@@ -31,7 +31,7 @@ def _particles(case_state):
 
 
 @pytest.mark.parametrize("method", ["update_particles_cpu", "update_particles_gpu"])
-def test_known_answer_cases(force_kats, method):
+def test_known_answer_cases(force_kats, method, ensemble_kernel):
     """Reference golden vectors through the drop-in NuclearForces methods."""
     from pyqmd_b200 import NuclearForces
     nf = NuclearForces()
@@ -77,7 +77,7 @@ def test_gpu_method_keeps_float32_attribute_types():
     assert ps[0].vx > 0 > ps[1].vx                           # p-p at d=3: net attraction (KAT-A)
 
 
-def test_u238_teacher_forced_1000_steps(u238_traj):
+def test_u238_teacher_forced_1000_steps(u238_traj, ensemble_kernel):
     """Config C1.  Each step both sides start from the same FP32-representable state (the
     device trajectory); per-step position and force errors are gated, branch-flip candidates
     counted; results go to gpurun_out/c1_parity.json."""
@@ -111,8 +111,8 @@ def test_u238_teacher_forced_1000_steps(u238_traj):
             assert w <= 1e-4, (s, w)
     assert amb_checked > 0.5 * amb_total
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "c1_parity.json"), "w") as f:
-        json.dump(dict(config="C1 U-238 teacher-forced", steps=1000, worst_pos_err=worst_pos,
+    with open(os.path.join(ROOT, "gpurun_out", f"c1_parity_{ensemble_kernel}.json"), "w") as f:
+        json.dump(dict(config="C1 U-238 teacher-forced", kernel=ensemble_kernel, steps=1000, worst_pos_err=worst_pos,
                        worst_force_err_l2=worst_f, ambiguous_nucleon_steps=amb_total,
                        ambiguous_checked_against_branch_alternatives=amb_checked,
                        ambiguous_worst_mismatch=amb_worst, tolerance=POS_TOL), f)
@@ -144,7 +144,7 @@ def test_u238_free_running_drift_report(u238_traj):
         json.dump(dict(config="C1 U-238 free-running drift (max |dx| / extent)", drift=report), f)
 
 
-def test_multi_step_kat_cases_teacher_forced(force_kats):
+def test_multi_step_kat_cases_teacher_forced(force_kats, ensemble_kernel):
     from pyqmd_b200.state import NucleusEnsemble
     for case in force_kats["cases"]:
         if case["steps"] == 1 or len(case["input"]["x"]) < 2:
@@ -163,7 +163,7 @@ def test_multi_step_kat_cases_teacher_forced(force_kats):
             assert force_error(ens.force.cpu().numpy(), fx, fy, amb) <= FORCE_TOL, case["name"]
 
 
-def test_fused_steps_equal_single_steps():
+def test_fused_steps_equal_single_steps(ensemble_kernel):
     """n sub-steps in one launch (state kept in shared memory) == n launches of one sub-step,
     bit for bit."""
     from pyqmd_b200.state import NucleusEnsemble, README_ISOTOPES
@@ -175,7 +175,7 @@ def test_fused_steps_equal_single_steps():
     assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
 
 
-def test_mixed_ensemble_against_oracle():
+def test_mixed_ensemble_against_oracle(ensemble_kernel):
     """All nine preset isotopes (A = 1 ... 238), several nuclei per block for the small ones,
     three teacher-forced steps against the oracle, per-nucleus norms."""
     from pyqmd_b200.state import NucleusEnsemble, README_ISOTOPES
@@ -201,7 +201,7 @@ def test_mixed_ensemble_against_oracle():
     print("mixed ensemble worst pos err", worst, "ambiguous", n_amb)
 
 
-def test_non_default_strengths_and_dt():
+def test_non_default_strengths_and_dt(ensemble_kernel):
     from pyqmd_b200.state import NucleusEnsemble
     rng = np.random.default_rng(5)
     n = 150

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 
 
 @pytest.mark.parametrize("seed", [11, 12])
-def test_random_nuclei_against_oracle(seed):
+def test_random_nuclei_against_oracle(seed, ensemble_kernel):
     import fuzz_forces
     res = fuzz_forces.run(seed, trials=10)
     assert res["nuclei"] == 480
