@@ -272,44 +272,55 @@ class HeadlessSimulation:
                                              step0))
         self.frames += 1
 
-    def free_particle_objects(self, k=None):
+    def free_particle_objects(self, k=None, types=None):
         """The emitted particles still alive as ``Particle`` objects (what the app keeps in
-        ``self.particles``, nuclear_sim.py:349); ``k``: only those emitted by nucleus ``k``."""
-        from .types import Particle
-        f = self.free
+        ``self.particles``, nuclear_sim.py:349); ``k``: only those emitted by nucleus ``k``.
+        ``types``: the module providing ``Particle`` / ``ParticleType`` (default: pyqmd_b200.types; pass
+        the reference's ``particles`` module to hand its own classes to its own ``Renderer``, which
+        compares ``particle.type`` with ITS enum, rendering.py:72,81)."""
+        from . import types as own
+        T = types or own
+        f = self.free_particles
         sel = np.arange(len(f["x"])) if k is None else np.nonzero(f["nucleus"] == k)[0]
         out = []
         for i in sel:
-            p = Particle(float(f["x"][i]), float(f["y"][i]), ParticleType(int(f["type"][i])),
-                         float(f["vx"][i]), float(f["vy"][i]))
+            p = T.Particle(float(f["x"][i]), float(f["y"][i]), T.ParticleType(int(f["type"][i])),
+                           float(f["vx"][i]), float(f["vy"][i]))
             p.age, p.lifetime = float(f["age"][i]), float(f["lifetime"][i])
             out.append(p)
         return out
 
-    def render_args(self, k=0, camera_pos=(400.0, 400.0), zoom=15.0):
+    def render_args(self, k=0, camera_pos=(400.0, 400.0), zoom=15.0, types=None):
         """Positional arguments of the reference's ``Renderer.render`` (rendering.py:32-34, called at
         nuclear_sim.py:598-603) for nucleus ``k``: pygame can draw the GPU-resident state with
-        ``renderer.render(*sim.render_args(k))``."""
-        return (self.nucleus_view(k), self.free_particle_objects(k), list(camera_pos), zoom,
+        ``renderer.render(*sim.render_args(k, types=particles))``."""
+        return (self.nucleus_view(k, types), self.free_particle_objects(k, types), list(camera_pos), zoom,
                 self.time_scale, self.accuracy, self.physics_dt, self.substeps_used, self.max_substeps,
                 True, dict(self.decay_counts), self.time_passed)
 
-    def nucleus_view(self, k=0):
-        """A ``Nucleus`` (pyqmd_b200.types) materialised from the device state of nucleus ``k`` --
-        the render bridge: ``Renderer`` reads ``.particles[i].x/.y/.type/.radius`` and
-        ``.protons/.neutrons/.stability`` (rendering.py:42-48, 135-246)."""
-        from .types import Nucleus, Particle
+    def nucleus_view(self, k=0, types=None):
+        """A ``Nucleus`` materialised from the device state of nucleus ``k`` -- the render bridge:
+        ``Renderer`` reads ``.particles[i].x/.y/.type/.radius`` and ``.protons/.neutrons/.stability``
+        (rendering.py:42-48, 135-246).  ``types``: see ``free_particle_objects``."""
+        from . import types as own
+        T = types or own
         ens = self.ensemble
         o, c = int(ens.offsets[k]), int(ens.count[k])
         pos = ens.pos[o:o + c].cpu().numpy().astype(np.float64)
         vel = ens.vel[o:o + c].cpu().numpy().astype(np.float64)
         isp = ens.is_proton[o:o + c].cpu().numpy()
         org = ens.origin[k].cpu().numpy() if ens.origin is not None else np.zeros(2)
-        ps = [Particle(float(p[0] + org[0]), float(p[1] + org[1]),
-                       ParticleType.PROTON if t else ParticleType.NEUTRON, float(v[0]), float(v[1]))
+        ps = [T.Particle(float(p[0] + org[0]), float(p[1] + org[1]),
+                         T.ParticleType.PROTON if t else T.ParticleType.NEUTRON, float(v[0]), float(v[1]))
               for p, v, t in zip(pos, vel, isp)]
         zn = int(ens.zn[k])
-        nuc = Nucleus(zn >> 16, zn & 0xFFFF, float(org[0]), float(org[1]), particles=ps)
+        if T is own:
+            nuc = own.Nucleus(zn >> 16, zn & 0xFFFF, float(org[0]), float(org[1]), particles=ps)
+        else:       # a foreign Nucleus class would lay out fresh particles in its constructor (particles.py:62)
+            nuc = object.__new__(T.Nucleus)
+            nuc.protons, nuc.neutrons = zn >> 16, zn & 0xFFFF
+            nuc.x, nuc.y = float(org[0]), float(org[1])
+            nuc.particles, nuc.decay_chain = ps, []
         nuc.update_center_of_mass()
         nuc.stability = float(ens.half_life[k])
         return nuc
