@@ -178,7 +178,7 @@ int pyqmd_cloud_sort_keys(const float *pos, const uint8_t *is_proton, int64_t n,
 #define PYQMD_TABLE_NDIM 192
 enum { PYQMD_HL_INF = 0, PYQMD_HL_TABLE = 1, PYQMD_HL_BAND = 2 };
 
-/* One (Z, N) row of the dense nuclide table, index Z * PYQMD_TABLE_NDIM + N.
+/* One (Z, N) row (88 bytes) of the dense nuclide table, index Z * PYQMD_TABLE_NDIM + N.
  * Built on the host from HALF_LIVES / DECAY_CHAINS and the two heuristics
  * (decay_chains.py:13-167, 169-201, 247-328) by pyqmd_b200/nuclides.py. */
 typedef struct {
@@ -192,7 +192,12 @@ typedef struct {
     int32_t opt_mode[2];/* PYQMD_DECAY_*                                                      */
     int32_t n_opt;      /* 1 or 2                                                             */
     int32_t kind;       /* PYQMD_HL_*                                                         */
+    uint64_t p_thr;     /* ceil(p_decay * 2^53): `random() < p` (particles.py:147) with random() =
+                           m / 2^53, m a 53-bit integer, is EXACTLY `m < p_thr` -- the decay-only
+                           kernel compares integers; 0 = stable, PYQMD_THR_PER_NUCLEUS for
+                           PYQMD_HL_BAND rows */
 } pyqmd_nuclide_entry;
+#define PYQMD_THR_PER_NUCLEUS 0xFFFFFFFFFFFFFFFFull
 
 /* One decay event (what handle_decay appends to self.particles, nuclear_sim.py:294,349). */
 typedef struct {

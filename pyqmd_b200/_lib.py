@@ -31,12 +31,13 @@ EXPORTS = (
     "pyqmd_population_step", "pyqmd_free_particles_frame",
 )
 
-# numpy mirror of pyqmd_nuclide_entry (80 bytes)
+# numpy mirror of pyqmd_nuclide_entry (88 bytes)
 NUCLIDE_DTYPE = np.dtype([
     ("half_life", "<f8"), ("p_decay", "<f8"), ("band_a", "<f8"), ("band_b", "<f8"),
     ("band_unit", "<f8"), ("opt_cum", "<f8", (2,)), ("opt_zn", "<i4", (2,)),
-    ("opt_mode", "<i4", (2,)), ("n_opt", "<i4"), ("kind", "<i4"),
+    ("opt_mode", "<i4", (2,)), ("n_opt", "<i4"), ("kind", "<i4"), ("p_thr", "<u8"),
 ], align=True)
+THR_PER_NUCLEUS = 0xFFFFFFFFFFFFFFFF
 
 # numpy mirror of pyqmd_decay_event (56 bytes)
 EVENT_DTYPE = np.dtype([
@@ -48,7 +49,7 @@ FREE_DTYPE = np.dtype([
     ("x", "<f8"), ("y", "<f8"), ("vx", "<f8"), ("vy", "<f8"), ("age", "<f8"), ("lifetime", "<f8"),
     ("nucleus", "<i8"), ("type", "<i4"), ("pad", "<i4"),
 ], align=True)
-assert NUCLIDE_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 56 and FREE_DTYPE.itemsize == 64
+assert NUCLIDE_DTYPE.itemsize == 88 and EVENT_DTYPE.itemsize == 56 and FREE_DTYPE.itemsize == 64
 
 
 class EnsembleDesc(C.Structure):

@@ -56,6 +56,17 @@ struct DrawSource {
     uint64_t seed;
     int64_t uniforms_n;       // nuclei per step in the uniforms array
 
+    // the same two draws as 53-bit integers m (u = m / 2^53): `u < p` is exactly `m < ceil(p 2^53)`
+    __device__ __forceinline__ void slot0_pair_bits(uint64_t pair_id, uint32_t step_abs, uint64_t& m_even,
+                                                    uint64_t& m_odd) const
+    {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)pair_id, (uint32_t)(pair_id >> 32), step_abs, 0u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), w);
+        m_even = ((uint64_t)(w[0] >> 5) << 26) | (uint64_t)(w[1] >> 6);
+        m_odd = ((uint64_t)(w[2] >> 5) << 26) | (uint64_t)(w[3] >> 6);
+    }
+
     // slot-0 draws of the nuclei 2 * pair_id and 2 * pair_id + 1 from one Philox call
     __device__ __forceinline__ void slot0_pair(uint64_t pair_id, uint32_t step_abs, double& u_even,
                                                double& u_odd) const
@@ -83,6 +94,12 @@ struct DrawSource {
         return (slot == 2) ? u53(w[2], w[3]) : u53(w[0], w[1]);
     }
 };
+
+// ceil(p 2^53) for a per-nucleus probability (estimated half-lives, caller-supplied values)
+__device__ __forceinline__ uint64_t decay_threshold(double p)
+{
+    return (p > 0.0) ? __double2ull_ru(p * 9007199254740992.0) : 0ull;
+}
 
 __device__ __forceinline__ const pyqmd_nuclide_entry* lookup(const pyqmd_nuclide_entry* table,
                                                               int32_t zn)

@@ -100,6 +100,14 @@ __device__ __forceinline__ Quad load_quad(const pyqmd_population& P, int64_t q, 
 // one block launch per 256 threads of useful work (ncu r02b: 32 % of the stall samples sat on the
 // first load, 9 % on the per-step barrier).  Decay counts go to a block-local table with shared-memory
 // atomics and are flushed once at the end.
+//
+// `random() < p` is decided in integers: the draw is the 53-bit integer m of CPython's m / 2^53, the
+// nuclide table carries p_thr = ceil(p 2^53), and m < p_thr is the same predicate exactly -- no
+// int -> float64 conversions, no float64 arithmetic on the every-step path (ncu r02d: 87 instructions
+// per nucleus-step, a third of them conversions, float64 compares and per-nucleus bookkeeping).
+// FAST = Philox draws, no per-nucleus `decided` output, every quad complete and 16-byte aligned: the
+// production case, without the predicates of the general one.
+template <bool FAST>
 __global__ void __launch_bounds__(kPopThreads, PYQMD_POP_MINBLOCKS) population_kernel(const pyqmd_population P,
                                                                     const int n_steps, const int64_t n_quads)
 {
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(kPopThreads, PYQMD_POP_MINBLOCKS) population_k
         __syncthreads();
     }
     const int n = (int)P.n;
-    const bool aligned = (P.id_base & 3) == 0;
+    const bool aligned = FAST || (P.id_base & 3) == 0;
     const DrawSource draws{P.uniforms, P.seed, P.uniforms_n};
     const int64_t stride = (int64_t)gridDim.x * kPopThreads;
     int64_t q = (int64_t)blockIdx.x * kPopThreads + threadIdx.x;
@@ -122,40 +130,47 @@ __global__ void __launch_bounds__(kPopThreads, PYQMD_POP_MINBLOCKS) population_k
         // prefetch: the next quad's words travel from DRAM while this one is processed (a second stage
         // for the dependent table-row loads was measured and did not pay: 2.19e11 vs 2.37e11 steps/s)
         if (q + stride < n_quads) cur = load_quad(P, q + stride, n, aligned);
-        const int i0 = (int)(kNPT * q - (P.id_base & 3));   // local index of the quad's first nucleus
-        const uint64_t quad = (uint64_t)(P.id_base >> 2) + (uint64_t)q;              // global quad id
+        const int i0 = (int)(kNPT * q - (FAST ? 0 : (P.id_base & 3)));   // local index of the first nucleus
+        const uint64_t quad = (uint64_t)(P.id_base >> 2) + (uint64_t)q;  // global quad id
         int32_t zn[kNPT];
-        double p[kNPT];
-        // per-step probability: the table row's, unless the half-life is a per-nucleus estimate (the
-        // row then holds NaN) or the caller supplied its own per-nucleus values
+        uint64_t thr[kNPT];
+        // threshold of the per-step probability: the table row's, unless the half-life is a per-nucleus
+        // estimate (the row says so) or the caller supplied its own per-nucleus values
 #pragma unroll
         for (int k = 0; k < kNPT; ++k) {
             zn[k] = me.zn[k];
-            p[k] = -1.0;
-            if (me.ok[k]) {
-                p[k] = row_of(P.table, zn[k])->p_decay;
-                if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || p[k] != p[k]) p[k] = P.p_decay[i0 + k];
+            thr[k] = 0;
+            if (FAST || me.ok[k]) {
+                thr[k] = row_of(P.table, zn[k])->p_thr;
+                if ((P.flags & PYQMD_POP_PER_NUCLEUS_STATE) || thr[k] == PYQMD_THR_PER_NUCLEUS)
+                    thr[k] = decay_threshold(P.p_decay[i0 + k]);
             }
         }
         for (int s = 0; s < n_steps; ++s) {
             const uint32_t step_abs = P.step0 + (uint32_t)s;
-            double u[kNPT];
-            if (P.uniforms) {
-#pragma unroll
-                for (int k = 0; k < kNPT; ++k) u[k] = me.ok[k] ? draws.one(0, i0 + k, step_abs, s, 0) : 1.0;
-            } else {
+            uint64_t m[kNPT] = {0, 0, 0, 0};
+            if (FAST || !P.uniforms) {
                 // unconditional (a stable nucleus ignores its draw): Philox does not wait for the loads
-                draws.slot0_pair(2 * quad, step_abs, u[0], u[1]);
-                draws.slot0_pair(2 * quad + 1, step_abs, u[2], u[3]);
+                draws.slot0_pair_bits(2 * quad, step_abs, m[0], m[1]);
+                draws.slot0_pair_bits(2 * quad + 1, step_abs, m[2], m[3]);
             }
 #pragma unroll
             for (int k = 0; k < kNPT; ++k) {
-                // stable (p < 0): no draw, decay_chains.py:403; otherwise random() < p, :421
-                const bool fired = me.ok[k] && p[k] >= 0.0 && u[k] < p[k];
-                if (P.decided && me.ok[k]) P.decided[(int64_t)s * n + i0 + k] = fired ? 1 : 0;
+                // stable (threshold 0): never; otherwise random() < p, decay_chains.py:421
+                bool fired;
+                if (!FAST && P.uniforms) {
+                    // parity path: caller-supplied doubles (not necessarily multiples of 2^-53) against
+                    // the nucleus' probability itself (the side array is kept current by pop_decay)
+                    const double p = (thr[k] == 0) ? -1.0 : P.p_decay[i0 + k];
+                    fired = me.ok[k] && p >= 0.0 && draws.one(0, i0 + k, step_abs, s, 0) < p;
+                } else {
+                    fired = (FAST || me.ok[k]) && m[k] < thr[k];
+                }
+                if (!FAST && P.decided && me.ok[k]) P.decided[(int64_t)s * n + i0 + k] = fired ? 1 : 0;
                 if (fired) {
-                    const DecayOut o = pop_decay(P, draws, i0 + k, zn[k], p[k], step_abs, s);
-                    zn[k] = o.zn; p[k] = o.p;
+                    const DecayOut o = pop_decay(P, draws, i0 + k, zn[k], 0.0, step_abs, s);
+                    zn[k] = o.zn;
+                    thr[k] = (o.mode == PYQMD_DECAY_NONE) ? thr[k] : decay_threshold(o.p);
                     if (o.mode != PYQMD_DECAY_NONE && P.step_counts) {
                         if (local_counts) {
                             atomicAdd(&scount[s][o.mode], 1u);
@@ -199,7 +214,11 @@ extern "C" int pyqmd_population_step(const pyqmd_population* p, int32_t n_steps,
     PYQMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t blocks = (n_quads + kPopThreads - 1) / kPopThreads;
     if (blocks > (int64_t)sms * PYQMD_POP_MINBLOCKS) blocks = (int64_t)sms * PYQMD_POP_MINBLOCKS;   // persistent grid
-    population_kernel<<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps, n_quads);
+    const bool fast = !p->uniforms && !p->decided && (p->id_base & 3) == 0 && (p->n & 3) == 0;
+    if (fast)
+        population_kernel<true><<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps, n_quads);
+    else
+        population_kernel<false><<<(unsigned)blocks, kPopThreads, 0, (cudaStream_t)stream>>>(*p, n_steps, n_quads);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;
 }

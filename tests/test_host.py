@@ -228,3 +228,27 @@ def test_dropin_recognises_protons_of_a_foreign_particle_class():
     assert forces._is_proton(P(ForeignType.PROTON)) and not forces._is_proton(P(ForeignType.NEUTRON))
     assert forces._is_proton(P(forces.ParticleType.PROTON)) and not forces._is_proton(P(forces.ParticleType.NEUTRON))
     assert forces._is_proton(P(0)) and not forces._is_proton(P(1))
+
+
+def test_integer_decay_threshold_is_the_same_predicate_as_random_lt_p():
+    """The decay-only kernel decides `random() < p` (particles.py:147) in integers: CPython's random()
+    is m / 2^53 for a 53-bit integer m, the table carries ceil(p * 2^53)."""
+    from pyqmd_b200 import nuclides
+    rng = np.random.default_rng(5)
+    p = np.concatenate([10.0 ** rng.uniform(-25, 0, 4000), rng.random(2000), [0.0, 1.0, 2.0 ** -53, 2.0 ** -60,
+                       float.fromhex("0x1.6b54e2b063e07p-11"), 0.5, 1.0 - 2.0 ** -53]])
+    thr = nuclides.decay_thresholds(p)
+    for k in range(len(p)):
+        t = int(thr[k])
+        cands = {0, 1, (1 << 53) - 1, max(t - 1, 0), t, min(t + 1, (1 << 53) - 1), int(rng.integers(0, 1 << 53))}
+        for m in cands:
+            assert ((m / 9007199254740992.0) < p[k]) == (m < t), (p[k], m, t)
+    assert nuclides.decay_thresholds(np.array([-1.0, np.nan]))[0] == 0
+    tab = nuclides.build_device_table(180825048000.0 * 1e-3)
+    band = tab["kind"] == _lib_mod().HL_BAND
+    assert (tab["p_thr"][band] == _lib_mod().THR_PER_NUCLEUS).all() and (tab["p_thr"][tab["p_decay"] < 0] == 0).all()
+
+
+def _lib_mod():
+    from pyqmd_b200 import _lib
+    return _lib
