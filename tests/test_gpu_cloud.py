@@ -352,3 +352,56 @@ def test_large_system_through_step_arrays_uses_the_sorted_symmetric_scheme():
     want = np.stack([x0[i0:i1], y0[i0:i1]], 1) + 0.85 * np.stack([fx, fy], 1) * dt * dt
     err = np.hypot(x[i0:i1] - want[:, 0], y[i0:i1] - want[:, 1]).max() / extent_of(pos)
     assert err <= POS_TOL
+
+
+# ---- the multi-GPU exchange on ONE device: virtual ranks ------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_symmetric_scheme_with_virtual_ranks_on_one_gpu(world):
+    """The strong-scaling path of bench.py -- rows dealt to `world` parts, one int64 accumulator array
+    per part, pyqmd_cloud_exchange_integrate pulling / clearing every part's accumulators and pushing the
+    new positions into every replica -- run with all parts on ONE device (the peers' pointer tables simply
+    point at buffers of the same GPU).  Must be bit-identical to the single-part step, for any `world`:
+    this keeps the fused exchange kernel under test on single-GPU boxes (tests/test_gpu_multi.py needs 2+)."""
+    import ctypes as C
+
+    from pyqmd_b200 import _lib
+    from pyqmd_b200.sharding import cloud_chunk, shard_range
+    from pyqmd_b200.state import NucleonCloud
+    n = 20_011
+    pos, isp = make_cloud(n, seed=21)
+    single = NucleonCloud(pos, isp)
+    single.step(2)
+    # sorted start state shared by all virtual ranks
+    ref = NucleonCloud(pos, isp)
+    dev = ref.device
+    lib = _lib.lib()
+    chunk = cloud_chunk(n, world)
+    padded = chunk * world
+    pos_a = [torch.zeros(padded, 2, device=dev) for _ in range(world)]
+    pos_b = [torch.zeros(padded, 2, device=dev) for _ in range(world)]
+    acc = [torch.zeros(padded, 2, dtype=torch.int64, device=dev) for _ in range(world)]
+    vel = [ref.vel.clone() for _ in range(world)]
+    ws = [torch.zeros_like(ref.workspace) for _ in range(world)]
+    for r in range(world):
+        pos_a[r][:n] = ref.pos[:n]
+    ptrs = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=dev)
+    acc_ptrs = ptrs(acc)
+    S, Cc, P = ref.strengths
+    st = _lib.current_stream()
+    for step in range(2):
+        cur, nxt = (pos_a, pos_b) if step % 2 == 0 else (pos_b, pos_a)
+        nxt_ptrs = ptrs(nxt)
+        for r in range(world):
+            _lib.check(lib.pyqmd_cloud_pair_forces(cur[r].data_ptr(), ref.is_proton.data_ptr(), n, r, world,
+                                                   S, Cc, P, acc[r].data_ptr(), ws[r].data_ptr(), st), "pair")
+        for r in range(world):
+            i0, i1 = shard_range(n, r, world)
+            _lib.check(lib.pyqmd_cloud_exchange_integrate(cur[r].data_ptr(), vel[r].data_ptr(), None, n, i0, i1,
+                                                          ref.dt, acc_ptrs.data_ptr(), nxt_ptrs.data_ptr(),
+                                                          world, ws[r].data_ptr(), st), "exchange")
+    final = pos_a if True else pos_b                      # two steps: back in pos_a
+    for r in range(world):
+        assert torch.equal(final[r][:n], single.pos[:n]), r      # every replica, bit for bit
+        assert int(acc[r].abs().max()) == 0                      # consumed entries were cleared
+    i0, i1 = shard_range(n, 1, world)
+    assert torch.equal(vel[1][i0:i1], single.vel[i0:i1])
