@@ -271,7 +271,9 @@ int pyqmd_ensemble_step(const pyqmd_ensemble *e, int32_t n_steps, void *stream);
  * flow through three in-order lanes (upload, compute, download) linked by events, so both copy
  * engines run back to back and the kernels hide under them.  Host arrays should be pinned.
  *   e          descriptor whose pointers are DEVICE buffers of the same layout (staging area)
- *   h_*        host arrays with the layout of e->pos, e->vel, e->is_proton, e->count, e->zn
+ *   h_*        host arrays with the layout of e->pos, e->vel, e->is_proton, e->count, e->zn;
+ *              h_is_proton may be NULL when decay is disabled (the types already on the device are
+ *              kept: without decay they cannot change, so one upload is enough)
  *   chunks     n_chunks descriptors: nuclei [nuc0, nuc1), slots [slot0, slot1) and the kernel
  *              launches of the chunk (one per size bin: cap, DEVICE index list, its length)
  * Stream-ordered on `stream`, non-blocking.

@@ -188,7 +188,8 @@ extern "C" int pyqmd_ensemble_step_host(const pyqmd_ensemble* e, float* h_pos, f
                                         int32_t n_steps, void* stream)
 {
     PYQMD_REQUIRE(e != nullptr && chunks != nullptr && n_chunks >= 0 && n_steps >= 0, "arguments");
-    PYQMD_REQUIRE(h_pos && h_vel && h_is_proton, "host arrays");
+    PYQMD_REQUIRE(h_pos && h_vel, "host arrays");
+    PYQMD_REQUIRE(h_is_proton || !e->decay_enabled, "h_is_proton may only be NULL when decay is disabled");
     PYQMD_REQUIRE(e->pos && e->vel && e->is_proton && e->offset && e->count, "device staging arrays");
     if (e->decay_enabled) PYQMD_REQUIRE(h_count && h_zn && e->zn, "count / zn arrays (decay enabled)");
     if (n_chunks == 0 || n_steps == 0) return PYQMD_OK;
@@ -210,8 +211,9 @@ extern "C" int pyqmd_ensemble_step_host(const pyqmd_ensemble* e, float* h_pos, f
                                          cudaMemcpyHostToDevice, g_pipe.up));
         PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->vel + 2 * c.slot0, h_vel + 2 * c.slot0, 8 * ns,
                                          cudaMemcpyHostToDevice, g_pipe.up));
-        PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->is_proton + c.slot0, h_is_proton + c.slot0, ns,
-                                         cudaMemcpyHostToDevice, g_pipe.up));
+        if (h_is_proton)      // types cannot change without decay: the caller may upload them once
+            PYQMD_CUDA_CHECK(cudaMemcpyAsync(e->is_proton + c.slot0, h_is_proton + c.slot0, ns,
+                                             cudaMemcpyHostToDevice, g_pipe.up));
         PYQMD_CUDA_CHECK(cudaEventRecord(g_pipe.ev_up[k], g_pipe.up));
         PYQMD_CUDA_CHECK(cudaStreamWaitEvent(g_pipe.run, g_pipe.ev_up[k], 0));
         for (int l = 0; l < c.n_launch; ++l) {

@@ -416,7 +416,9 @@ class HostEnsembleRunner:
             rows.append(c)
         self.n_chunks = len(rows)
         self.chunk_array = (_lib.HostChunk * self.n_chunks)(*rows)
-        self.h2d_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes + self.h_isp.nbytes)
+        # without decay the nucleon types never change: they are uploaded with the first step only
+        self.types_resident = False
+        self.h2d_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes) + (int(self.h_isp.nbytes) if ens.decay else 0)
         # without decay the types / counts / (Z, N) cannot change: only positions and velocities
         # come back, like the reference's download (nuclear_forces.py:227)
         self.d2h_bytes = int(self.h_pos.nbytes + self.h_vel.nbytes) + (
@@ -426,8 +428,10 @@ class HostEnsembleRunner:
     def step(self, n_steps=1):
         ens = self.ens
         d = ens._desc(1, None, 0, None)
+        isp_ptr = None if (self.types_resident and not ens.decay) else self.h_isp.data_ptr()
+        self.types_resident = True
         _lib.check(_lib.lib().pyqmd_ensemble_step_host(
-            C.byref(d), self.h_pos.data_ptr(), self.h_vel.data_ptr(), self.h_isp.data_ptr(),
+            C.byref(d), self.h_pos.data_ptr(), self.h_vel.data_ptr(), isp_ptr,
             self.h_count.data_ptr(), self.h_zn.data_ptr(), self.chunk_array, self.n_chunks, n_steps,
             _lib.current_stream()), "pyqmd_ensemble_step_host")
         ens.step_index += n_steps

@@ -8,8 +8,8 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 python - <<PY
 import json
 d = json.loads([l for l in open("gpurun_out/bench_g$N.json") if l.startswith("{")][-1])
-print("N=$N value %.4g ms %.3f e2e %.4g exchange %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["config"]["exchange"]))
-print({k: d["config"].get(k) for k in ("pair_kernel_ms_per_rank", "pair_kernel_imbalance", "step_ms_outside_pair_kernel")})
+print("N=$N value %.4g ms %.3f e2e %.4g exchange %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["details"]["exchange_used"]))
+print({k: d["details"].get(k) for k in ("pair_kernel_ms_per_rank", "pair_kernel_imbalance", "step_ms_outside_pair_kernel")})
 PY
 done
 for W in decay mixed ensemble; do

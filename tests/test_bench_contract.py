@@ -51,12 +51,23 @@ def test_reference_arm_falls_back_to_the_port_without_the_reference():
 
 
 def test_both_arms_describe_the_same_config():
+    """`config` comes from one function of the command line only, so the reference arm and ours print the
+    same object for the same flags (measured details of our arm go to `details`)."""
     sys.path.insert(0, ROOT)
-    import bench
-    a = bench.parse.__globals__["workload_config"]
     import argparse
-    ns = argparse.Namespace(workload="cloud", gpus=4, cloud_n=1_000_000, nuclei=0)
-    assert a(ns) == a(ns) and a(ns)["gpus"] == 4
+
+    import bench
+    ns = argparse.Namespace(workload="cloud", gpus=4, cloud_n=1_000_000, nuclei=0, cloud_scheme="symmetric",
+                            cloud_exchange="peer")
+    cfg = bench.workload_config(ns)
+    assert cfg == bench.workload_config(ns) and cfg["gpus"] == 4 and cfg["exchange"] == "peer"
+    assert "l2_policy" in cfg and "model" not in cfg
+    ns.gpus = 1
+    assert bench.workload_config(ns)["exchange"].startswith("none")
+    r = run("--impl", "reference", "--steps", "1", "--warmup", "0", "--gpus", "4", env={"PYQMD_NO_REF": "1"})
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    ns.gpus = 4
+    assert d["config"] == bench.workload_config(ns)
 
 
 def test_reference_arm_other_ranks_exit_without_work():
