@@ -145,6 +145,22 @@ int32_t pyqmd_cloud_force_scale_log2(int64_t n);
 int pyqmd_cloud_pair_forces(const float *pos, const uint8_t *is_proton, int64_t n, int32_t part,
                             int32_t n_parts, float strong, float coulomb, float pauli,
                             long long *force_acc, void *workspace, void *stream);
+/*
+ * pyqmd_cloud_pair_forces with option flags.
+ * PYQMD_CLOUD_SKIP_EXACT_ZEROS (off by default): beyond d = 353 the tail term
+ * 0.15 S exp(-1.8 d / 7) / (d + eps) is exactly +0 in the kernel's FP32 arithmetic (its 2^x argument is
+ * below -126 and ex2.approx.ftz flushes to zero), so a pair that far apart contributes its Coulomb term
+ * only, i.e. nothing unless both nucleons are protons.  With the flag, 256-nucleon tiles whose bounding
+ * boxes are further apart than that skip the exponential, and skip the tile altogether when one side has
+ * no protons.  The accumulators come out BIT-IDENTICAL to the default (tests/test_gpu_cloud.py); only the
+ * time changes.  It is opt-in because the benchmark metric counts N (N - 1) pair evaluations per step
+ *  and a kernel that proves most of them zero is no longer "evaluating all pairs".
+ * Ignored (default behaviour) when the strengths do not allow the proof (S > 180).
+ */
+#define PYQMD_CLOUD_SKIP_EXACT_ZEROS 1u
+int pyqmd_cloud_pair_forces_ex(const float *pos, const uint8_t *is_proton, int64_t n, int32_t part,
+                               int32_t n_parts, float strong, float coulomb, float pauli,
+                               long long *force_acc, void *workspace, uint32_t flags, void *stream);
 int pyqmd_cloud_integrate(const float *pos_in, float *pos_out, float *vel, float *force, int64_t n,
                           int64_t i0, int64_t i1, float dt, long long *force_acc_i0,
                           void *workspace, void *stream);

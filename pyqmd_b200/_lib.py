@@ -24,7 +24,7 @@ EXPORTS = (
     "pyqmd_fp32_peak",
     "pyqmd_update_forces_and_positions", "pyqmd_update_particles_f64", "pyqmd_cloud_step_host",
     "pyqmd_cloud_workspace_bytes", "pyqmd_cloud_step", "pyqmd_cloud_sort_keys",
-    "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_integrate",
+    "pyqmd_cloud_force_scale_log2", "pyqmd_cloud_pair_forces", "pyqmd_cloud_pair_forces_ex", "pyqmd_cloud_integrate",
     "pyqmd_cloud_exchange_integrate",
     "pyqmd_ensemble_step", "pyqmd_ensemble_step_host", "pyqmd_resolve_overlaps", "pyqmd_ensemble_census",
     "pyqmd_ensemble_init_layout",
@@ -96,6 +96,7 @@ class PopulationDesc(C.Structure):
 
 
 POP_PER_NUCLEUS_STATE = 1
+CLOUD_SKIP_EXACT_ZEROS = 1
 
 
 class FreeFrame(C.Structure):
@@ -135,6 +136,7 @@ def lib():
     L.pyqmd_cloud_sort_keys.argtypes = [vp, vp, i64, f32, f32, f32, vp, vp]
     L.pyqmd_cloud_force_scale_log2.argtypes = [i64]
     L.pyqmd_cloud_pair_forces.argtypes = [vp, vp, i64, i32, i32, f32, f32, f32, vp, vp, vp]
+    L.pyqmd_cloud_pair_forces_ex.argtypes = [vp, vp, i64, i32, i32, f32, f32, f32, vp, vp, C.c_uint32, vp]
     L.pyqmd_cloud_integrate.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, vp, vp, vp]
     L.pyqmd_cloud_exchange_integrate.argtypes = [vp, vp, vp, i64, i64, i64, f32, vp, vp, i32, vp, vp]
     L.pyqmd_ensemble_step.argtypes = [C.POINTER(EnsembleDesc), i32, vp]

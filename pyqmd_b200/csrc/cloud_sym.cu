@@ -42,11 +42,21 @@ struct SymParams {
     int part, n_parts;
     int tiles_per_unit;
     int far_enabled;
+    int skip_exact_zeros;             // PYQMD_CLOUD_SKIP_EXACT_ZEROS
     float scale;                      // 2^k, fixed-point scale of the accumulators
 };
 
+// Beyond this bounding-box gap the tail term 0.15 S exp(-1.8 d / 7) / (d + eps) is EXACTLY zero in the
+// arithmetic of far_pair2_sym: its exponent argument log2(0.15 S) - 0.371 d (+ a correction < 1e-3) is
+// below -126, and ex2.approx.ftz flushes 2^x to +0 there.  What is left of such a pair is the Coulomb
+// term (p-p only).  d >= 353 covers every S <= 180 (log2(0.15 S) <= 4.76); the host checks the bound and
+// ignores the flag otherwise.
+constexpr float kUltraGap = 353.0f;
+
 // Two far pairs (one i, two j), action on i and (REACT) reaction on the two j.
-template <int MODE, bool REACT>
+// NOEXP (MODE 1 / 2 only): the caller has proved that the tail term is exactly zero (kUltraGap), so
+// s = r2 ((q r) g + 0): the same bits as the full expression, without its exponential.
+template <int MODE, bool REACT, bool NOEXP = false>
 __device__ __forceinline__ void far_pair2_sym(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
                                               const FarConsts& c, f32x2& fx, f32x2& fy, f32x2& rx,
                                               f32x2& ry)
@@ -56,10 +66,13 @@ __device__ __forceinline__ void far_pair2_sym(f32x2 xj, f32x2 yj, f32x2 xi, f32x
     float a0, a1;
     upk(d2, a0, a1);
     const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
-    f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
-    arg = fma2(r, fma2(r, c.l2, c.l1), arg);
-    upk(arg, a0, a1);
-    const f32x2 e = pk(mufu_ex2(a0), mufu_ex2(a1));
+    f32x2 e = 0ull;
+    if (!NOEXP) {
+        f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
+        arg = fma2(r, fma2(r, c.l2, c.l1), arg);
+        upk(arg, a0, a1);
+        e = pk(mufu_ex2(a0), mufu_ex2(a1));
+    }
     const f32x2 r2 = mul2(r, r);
     f32x2 s;
     if (MODE == 0) {
@@ -78,8 +91,8 @@ __device__ __forceinline__ void far_pair2_sym(f32x2 xj, f32x2 yj, f32x2 xi, f32x
 }
 
 // One 32-step sweep of a warp's 128 i-nucleons over a 128-nucleon half tile.
-//   PATH 0/1/2: far field, MODE = PATH;  PATH 3: general law.
-template <int PATH, bool REACT>
+//   PATH 0/1/2: far field, MODE = PATH;  PATH 3: general law.  NOEXP: see far_pair2_sym.
+template <int PATH, bool REACT, bool NOEXP = false>
 __device__ __forceinline__ void sweep_half(const float* __restrict__ sx, const float* __restrict__ sy,
                                            const float* __restrict__ st, int lane,
                                            const float (&xi)[kIPT], const float (&yi)[kIPT],
@@ -114,12 +127,12 @@ __device__ __forceinline__ void sweep_half(const float* __restrict__ sx, const f
             }
 #pragma unroll
             for (int k = 0; k < kIPT; ++k) {
-                far_pair2_sym<PATH, REACT>(X.x, Y.x, xi2[k], yi2[k],
-                                           PATH == 2 ? mul2(nq2[k], T01) : 0ull, c, ax[k], ay[k], rx01,
-                                           ry01);
-                far_pair2_sym<PATH, REACT>(X.y, Y.y, xi2[k], yi2[k],
-                                           PATH == 2 ? mul2(nq2[k], T23) : 0ull, c, ax[k], ay[k], rx23,
-                                           ry23);
+                far_pair2_sym<PATH, REACT, NOEXP>(X.x, Y.x, xi2[k], yi2[k],
+                                                  PATH == 2 ? mul2(nq2[k], T01) : 0ull, c, ax[k], ay[k],
+                                                  rx01, ry01);
+                far_pair2_sym<PATH, REACT, NOEXP>(X.y, Y.y, xi2[k], yi2[k],
+                                                  PATH == 2 ? mul2(nq2[k], T23) : 0ull, c, ax[k], ay[k],
+                                                  rx23, ry23);
             }
             if (REACT) {                   // the accumulators follow their j group to lane - 1
                 rx01 = shfl64(rx01, nxt); ry01 = shfl64(ry01, nxt);
@@ -170,12 +183,22 @@ __device__ __forceinline__ void sweep_half(const float* __restrict__ sx, const f
     }
 }
 
+// path 0..3 as sweep_half; 4: every pair of the tile is exactly zero (tail underflow, no p-p pair);
+// 5 / 6: MODE 1 / 2 without the exponential.
 template <bool REACT>
 __device__ __forceinline__ void sweep_tile(int path, const float* sx, const float* sy, const float* st,
                                            int lane, const float (&xi)[kIPT], const float (&yi)[kIPT],
                                            const float (&ti)[kIPT], float (&fx)[kIPT], float (&fy)[kIPT],
                                            const LawParams& L, float2* row)
 {
+    if (path == 4) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) { fx[k] = 0.f; fy[k] = 0.f; }
+        if (REACT)                                           // the flush sums all eight warp rows
+            for (int k = lane; k < kTile / 2; k += 32)
+                reinterpret_cast<float4*>(row)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     f32x2 ax[kIPT], ay[kIPT];
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) { ax[k] = 0ull; ay[k] = 0ull; }
@@ -188,6 +211,8 @@ __device__ __forceinline__ void sweep_tile(int path, const float* sx, const floa
         if (path == 0) sweep_half<0, REACT>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
         else if (path == 1) sweep_half<1, REACT>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
         else if (path == 2) sweep_half<2, REACT>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
+        else if (path == 5) sweep_half<1, REACT, true>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
+        else if (path == 6) sweep_half<2, REACT, true>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
         else sweep_half<3, REACT>(hx, hy, ht, lane, xi, yi, ti, ax, ay, L, hr);
     }
 #pragma unroll
@@ -300,10 +325,17 @@ cloud_sym_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp
         const int tf = w.flags[tile];
         const float gx = fmaxf(0.f, fmaxf(bb.x - bxmax, bxmin - bb.z));
         const float gy = fmaxf(0.f, fmaxf(bb.y - bymax, bymin - bb.w));
-        const bool far = sp.far_enabled && (fmaf(gx, gx, gy * gy) > 81.01f);
-        const int path = !far ? 3
-                         : ((alln || (tf & kTileAllNeutron)) ? 0
-                            : ((allp && (tf & kTileAllProton)) ? 1 : 2));
+        const float gap2 = fmaf(gx, gx, gy * gy);
+        const bool far = sp.far_enabled && (gap2 > 81.01f);
+        int path = !far ? 3
+                   : ((alln || (tf & kTileAllNeutron)) ? 0
+                      : ((allp && (tf & kTileAllProton)) ? 1 : 2));
+        if (far && sp.skip_exact_zeros && gap2 > kUltraGap * kUltraGap) path = (path == 0) ? 4 : path + 4;
+        // the whole block agrees that every pair of this tile is exactly zero: no sweep, no flush
+        if (sp.skip_exact_zeros && __syncthreads_and(path == 4)) {
+            prev_react = false;
+            continue;
+        }
         if (diag)
             sweep_tile<false>(path, sxb[buf], syb[buf], stb[buf], lane, xi, yi, ti, fx, fy, L, nullptr);
         else
@@ -410,6 +442,15 @@ extern "C" int pyqmd_cloud_pair_forces(const float* pos, const uint8_t* is_proto
                                        int32_t part, int32_t n_parts, float strong, float coulomb,
                                        float pauli, long long* force_acc, void* workspace, void* stream)
 {
+    return pyqmd_cloud_pair_forces_ex(pos, is_proton, n, part, n_parts, strong, coulomb, pauli, force_acc,
+                                      workspace, 0u, stream);
+}
+
+extern "C" int pyqmd_cloud_pair_forces_ex(const float* pos, const uint8_t* is_proton, int64_t n,
+                                          int32_t part, int32_t n_parts, float strong, float coulomb,
+                                          float pauli, long long* force_acc, void* workspace,
+                                          uint32_t flags, void* stream)
+{
     PYQMD_REQUIRE(n >= 0 && n_parts >= 1 && part >= 0 && part < n_parts, "0 <= part < n_parts");
     if (n == 0) return PYQMD_OK;
     PYQMD_REQUIRE(pos && is_proton && force_acc && workspace, "NULL pointer");
@@ -427,6 +468,9 @@ extern "C" int pyqmd_cloud_pair_forces(const float* pos, const uint8_t* is_proto
     sp.part = part;
     sp.n_parts = n_parts;
     sp.far_enabled = (strong > 0.f && !L.far_needs_clamp) ? 1 : 0;
+    // exact-zero skipping needs the tail exponent below the flush-to-zero point at the ultra-far gap
+    const float arg_at_gap = L.log2TailK + kUltraGap * (-1.8f * kLog2e / 7.0f);
+    sp.skip_exact_zeros = ((flags & PYQMD_CLOUD_SKIP_EXACT_ZEROS) && sp.far_enabled && arg_at_gap < -126.2f) ? 1 : 0;
     sp.scale = ldexpf(1.0f, scale_log2_for(n));
     // ~96 units per resident-block slot of this part (148 SMs x 2), 4..64 tiles each: the hardware
     // hands blocks to SMs as slots free up, so the idle tail of a launch is about half a unit -- 0.5 %

@@ -464,7 +464,8 @@ class NucleonCloud:
 
     def __init__(self, pos, is_proton, vel=None, *, device="cuda", dt=DEFAULT_DT,
                  strengths=DEFAULT_STRENGTHS, rank=0, world=1, group=None, sort=True,
-                 keep_force=False, scheme="symmetric", exchange="peer", allow_nccl_fallback=False):
+                 keep_force=False, scheme="symmetric", exchange="peer", allow_nccl_fallback=False,
+                 skip_exact_zeros=False):
         _lib.require_cuda()
         assert scheme in ("symmetric", "ordered") and exchange in ("peer", "nccl")
         dev = self.device = torch.device(device)
@@ -476,6 +477,9 @@ class NucleonCloud:
         self.dt, self.strengths = float(dt), tuple(float(s) for s in strengths)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.scheme = scheme
+        # opt-in: skip tiles / exponentials whose contribution is exactly zero in FP32 (bit-identical
+        # results, see PYQMD_CLOUD_SKIP_EXACT_ZEROS in include/pyqmd_b200.h)
+        self.pair_flags = _lib.CLOUD_SKIP_EXACT_ZEROS if skip_exact_zeros else 0
         self.chunk = cloud_chunk(self.n, self.world)
         self.i0, self.i1 = shard_range(self.n, self.rank, self.world)
         self.perm = None
@@ -571,9 +575,9 @@ class NucleonCloud:
                 if self.profile is not None:     # per-rank kernel time (load-balance evidence)
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
-                _lib.check(lib.pyqmd_cloud_pair_forces(
+                _lib.check(lib.pyqmd_cloud_pair_forces_ex(
                     self.pos.data_ptr(), self.is_proton.data_ptr(), self.n, self.rank, self.world,
-                    S, Cc, P, self.acc.data_ptr(), self.workspace.data_ptr(), stream),
+                    S, Cc, P, self.acc.data_ptr(), self.workspace.data_ptr(), self.pair_flags, stream),
                     "pyqmd_cloud_pair_forces")
                 if self.profile is not None:
                     ev[1].record()

