@@ -159,8 +159,9 @@ class FreeParticlePool:
     one app frame and absorbs the ensemble's decay events of that frame; it never synchronises."""
 
     def __init__(self, device, capacity=1 << 20):
+        from .state import resolve_device
         import torch
-        self.device, self.capacity = torch.device(device), int(capacity)
+        self.device, self.capacity = resolve_device(device), int(capacity)
         nbytes = self.capacity * _lib.FREE_DTYPE.itemsize
         self.buf = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.count = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(2)]

@@ -37,11 +37,22 @@ _TEMPLATES = None
 _TABLE_CACHE = {}
 
 
+def resolve_device(device) -> torch.device:
+    """``torch.device`` with an explicit index ("cuda" means the device that is current NOW)."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
 def _on_device(fn):
     """Run a method with ``self.device`` as the current CUDA device: the C ABI launches on the
     current device's stream, so pointers of another device must never meet it."""
     @functools.wraps(fn)
     def wrapper(self, *args, **kwargs):
+        idx = self.device.index
+        if idx is None or idx == torch.cuda.current_device():      # the common case: nothing to switch
+            return fn(self, *args, **kwargs)
         with torch.cuda.device(self.device):
             return fn(self, *args, **kwargs)
     return wrapper
@@ -113,7 +124,7 @@ class NucleusEnsemble:
                  id_base=0, half_life=None, p_decay=None, origin=None, decay=True,
                  event_capacity=1 << 20, init_seed=0, keep_force=False):
         _lib.require_cuda()
-        self.device = torch.device(device)
+        self.device = resolve_device(device)
         dev = self.device
         as_t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray)
                                              else a, dtype=dt).contiguous().to(dev)
@@ -468,7 +479,7 @@ class NucleonCloud:
                  skip_exact_zeros=False):
         _lib.require_cuda()
         assert scheme in ("symmetric", "ordered") and exchange in ("peer", "nccl")
-        dev = self.device = torch.device(device)
+        dev = self.device = resolve_device(device)
         pos = torch.as_tensor(pos, dtype=torch.float32).reshape(-1, 2).to(dev)
         isp = torch.as_tensor(is_proton, dtype=torch.uint8).to(dev)
         vel = torch.zeros_like(pos) if vel is None else torch.as_tensor(
@@ -665,7 +676,7 @@ class DecayPopulation:
     def __init__(self, zn, *, device="cuda", dt_decay, seed=0, id_base=0, watch=(),
                  half_life=None, p_decay=None, init_seed=0):
         _lib.require_cuda()
-        dev = self.device = torch.device(device)
+        dev = self.device = resolve_device(device)
         self.zn = torch.as_tensor(zn, dtype=torch.int32).contiguous().to(dev)
         check_table_range(self.zn)
         self.n = int(self.zn.numel())
