@@ -97,14 +97,11 @@ def admissible_force_check(pos32, isp, f_dev, fx, fy, amb, S=150.0, C=30.0, P=35
         near[i] = False
         for j, t in zip(*np.nonzero(near)):
             thr = THRESHOLDS[t]
-            if True:
-                if True:
-                    cur = pair_net(d[j], isp[i], isp[j], S, C, P)
-                    other = pair_net(thr * (1 + 8 * tol) if d[j] < thr else thr * (1 - 8 * tol), isp[i], isp[j],
-                                     S, C, P)
-                    c = 0.0 if cur is None else cur
-                    o = 0.0 if other is None else other
-                    alts.append(((o - c) * dx[j] / d[j], (o - c) * dy[j] / d[j]))
+            cur = pair_net(d[j], isp[i], isp[j], S, C, P)
+            other = pair_net(thr * (1 + 8 * tol) if d[j] < thr else thr * (1 - 8 * tol), isp[i], isp[j], S, C, P)
+            c = 0.0 if cur is None else cur
+            o = 0.0 if other is None else other
+            alts.append(((o - c) * dx[j] / d[j], (o - c) * dy[j] / d[j]))
         if not alts or len(alts) > 6:
             continue
         best = np.inf
