@@ -221,3 +221,43 @@ def test_free_particle_pool_follows_the_host_mirror_over_frames():
         assert np.allclose(dev[key], host[key][order], rtol=1e-15, atol=0), key
     assert np.array_equal(dev["nucleus"], host["nucleus"][order])
     assert hs.events_dropped == 0
+
+
+def test_spawned_particles_get_the_reference_speed_and_lifetime():
+    """handle_decay's rewrite of a fresh product (nuclear_sim.py:295-342) on the device, against the
+    goldens generated from the reference (`cosmetics`: lifetime per (time scale, sub-steps, physics dt,
+    particle type), speed renormalised to 30 / 50 / 60 / 40): events are written into a device event log
+    by hand and absorbed by pyqmd_free_particles_frame."""
+    import types as pytypes
+
+    from conftest import load_json
+    from pyqmd_b200 import _lib
+    from pyqmd_b200.sim import FreeParticlePool, frame_constants
+    gold = load_json("sim_driver.json.gz")["cosmetics"]
+    fh = float.fromhex
+    groups = {}
+    for row in gold:
+        groups.setdefault((row["time_scale"], row["substeps"], row["physics_dt"]), []).append(row)
+    speeds = {ParticleType.ALPHA.value: 30.0, ParticleType.GAMMA.value: 60.0,
+              ParticleType.ELECTRON.value: 50.0, ParticleType.POSITRON.value: 50.0}
+    checked = 0
+    for (ts, sub, pdt), rows in groups.items():
+        ev = np.zeros(len(rows), _lib.EVENT_DTYPE)
+        for k, row in enumerate(rows):
+            ev[k]["nucleus"], ev[k]["step"], ev[k]["ptype"] = k, sub - 1, row["ptype"]      # born in the last sub-step
+            ev[k]["x"], ev[k]["y"] = 400.0 + k, 400.0
+            ev[k]["vx"], ev[k]["vy"] = 3.0 * fh(row["vx"]), 3.0 * fh(row["vy"])              # same direction, other speed
+        buf = torch.from_numpy(ev.view(np.uint8).reshape(-1).copy()).cuda()
+        fake = pytypes.SimpleNamespace(events_buf=buf, event_capacity=len(rows),
+                                       event_count=torch.tensor([len(rows)], dtype=torch.int64, device="cuda"))
+        pool = FreeParticlePool("cuda", capacity=256)
+        pool.frame(fake, frame_constants(fh(ts), sub, 1 / 240, 0.004, fh(pdt), step0=0))
+        rec = pool.download()
+        assert len(rec) == len(rows) and int(fake.event_count.item()) == 0
+        for row, r in zip(rows, rec[np.argsort(rec["nucleus"])]):
+            assert r["lifetime"] == fh(row["lifetime"]), row
+            assert abs(np.hypot(r["vx"], r["vy"]) - speeds.get(row["ptype"], 40.0)) < 1e-9
+            assert np.allclose([r["vx"], r["vy"]], [fh(row["vx"]), fh(row["vy"])], rtol=1e-12)
+            assert r["age"] == 0.0 and r["x"] == 400.0 + r["nucleus"]
+            checked += 1
+    assert checked == len(gold) and checked > 100
