@@ -351,3 +351,28 @@ def test_single_system_sizes_through_the_host_api(n):
     # force gate: from rest v' = 0.85 F dt (nuclear_forces.py:312-319), so F is read off the velocity
     f_dev = np.stack([vx, vy], 1) / (0.85 / 240)
     assert force_error(f_dev, fx, fy, amb) <= FORCE_TOL
+
+
+@pytest.mark.parametrize("n", [257, 300, 384, 400, 511, 512])
+def test_ring_kernel_with_three_and_four_warps_per_nucleus(n, monkeypatch):
+    """The warp-local ring kernel at 3 and 4 groups per nucleus (257..512 nucleons; the automatic dispatch
+    only takes it there for large launches): odd and even group counts, full and half off-diagonal blocks."""
+    monkeypatch.setenv("PYQMD_ENSEMBLE_KERNEL", "ring")
+    rng = np.random.default_rng(n)
+    R = 2.2 * np.sqrt(n)
+    r, th = R * np.sqrt(rng.random(n)), 2 * np.pi * rng.random(n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32)
+    vel = (rng.standard_normal((n, 2)) * 0.1).astype(np.float32)
+    isp = (rng.random(n) < 0.4).astype(np.uint8)
+    ens = single_nucleus_ensemble(pos, vel, isp)
+    ox, oy, ovx, ovy, fx, fy, amb = oracle_step(pos, vel, isp, ens.dt_phys)
+    ens.step(1)
+    assert pos_error(pos, ens.pos.cpu().numpy(), ox, oy, amb) <= POS_TOL
+    assert force_error(ens.force.cpu().numpy(), fx, fy, amb) <= FORCE_TOL
+    # three fused sub-steps == three single ones (state kept in shared memory / registers in between)
+    a = single_nucleus_ensemble(pos, vel, isp)
+    b = single_nucleus_ensemble(pos, vel, isp)
+    a.step(3)
+    for _ in range(3):
+        b.step(1)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
