@@ -55,7 +55,7 @@ def state_of(sim):
             [p.type.value for p in ps])
 
 
-def run_teacher_forced(ref, frames, time_scale, method, seed):
+def run_teacher_forced(ref, frames, time_scale, method, seed, isotope=(92, 146)):
     """Sim A = the reference's CPU path, sim B = the same application code over pyqmd_b200.NuclearForces.
     Every frame B restarts from A's state and RNG state.  Returns, per frame, the position error after the
     sub-steps (BEFORE resolve_overlaps: the hot path itself), after the whole frame, the velocity error
@@ -66,7 +66,7 @@ def run_teacher_forced(ref, frames, time_scale, method, seed):
     gpu_forces = ns.NuclearForces()
     random.seed(seed)
     a = headless(ns, ref.forces(), gpu_available=False)      # reference CPU path (:173)
-    a.create_nucleus(92, 146)                                # nuclear_sim.py:92-116
+    a.create_nucleus(*isotope)                               # nuclear_sim.py:92-116
     a.time_scale = time_scale
     b = headless(ns, gpu_forces, gpu_available=(method == "gpu"))   # :171 update_particles_gpu / :173 _cpu
     # Nucleons with a partner within AMB (relative) of a discontinuity of the law (d^2 = 0.01, d = 2.8,
@@ -150,3 +150,18 @@ def test_reference_update_simulation_with_decays_on_the_dropin(ref):
     print(f"reference app with decays: position error before the projection max {pre.max():.2e} "
           f"(20 free-running sub-steps per frame), decays {decays[-1] - 1}")
     assert np.isfinite(post).all() and pre.max() <= 1e-3      # 20 free-running sub-steps through a whole decay chain (measured 1.8e-4)
+
+
+@pytest.mark.parametrize("isotope,time_scale,min_decays", [
+    ((6, 8), 180825048000.0 * 60 / 3, 1),            # C-14: beta-minus within a few frames, then stable N-14
+    ((84, 134), 186.0 * 60 * 4, 1),                  # Po-218: the two-option branch (alpha 99.98 % / beta-minus)
+    ((26, 30), 1.0, 0),                              # Fe-56: stable, the sub-warp ring / block kernels at A = 56
+])
+def test_reference_app_other_presets_on_the_dropin(ref, isotope, time_scale, min_decays):
+    """The same teacher-forced comparison for other nuclei of the app's preset list (nuclear_sim.py:494-504):
+    light and medium nuclei take other kernel geometries, C-14 and Po-218 decay through other modes."""
+    pre, post, verrs, decays, excl = run_teacher_forced(ref, 12, time_scale, "cpu", seed=3, isotope=isotope)
+    print(f"reference app, isotope {isotope}: position error before the projection max {pre.max():.2e}, "
+          f"decays {decays[-1] - 1}")
+    assert decays[-1] - 1 >= min_decays
+    assert np.isfinite(post).all() and pre.max() <= (4e-5 if min_decays == 0 else 1e-3)
