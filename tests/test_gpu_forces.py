@@ -376,3 +376,32 @@ def test_ring_kernel_with_three_and_four_warps_per_nucleus(n, monkeypatch):
     for _ in range(3):
         b.step(1)
     assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
+
+
+@pytest.mark.parametrize("n", [600, 1000])
+def test_opencl_shaped_entry_point_with_a_large_particle_list(n):
+    """update_particles_gpu (float32 [n][4] buffers + caller-supplied centre, nuclear_forces.py:190-219)
+    for 513..1024 particles: the ring kernel with 5..8 warps and the `center` argument."""
+    from pyqmd_b200 import NuclearForces, Particle, ParticleType
+    rng = np.random.default_rng(n)
+    R = 2.5 * np.sqrt(n)
+    r, th = R * np.sqrt(rng.random(n)), 2 * np.pi * rng.random(n)
+    # FP32-representable absolute coordinates around the app's origin (400, 400), nuclear_sim.py:93
+    x32 = (400.0 + r * np.cos(th)).astype(np.float32)
+    y32 = (400.0 + r * np.sin(th)).astype(np.float32)
+    isp = (rng.random(n) < 0.4).astype(np.uint8)
+    ps = [Particle(float(a), float(b), ParticleType.PROTON if t else ParticleType.NEUTRON)
+          for a, b, t in zip(x32, y32, isp)]
+    NuclearForces().update_particles_gpu(ps, 1 / 240)
+    x, y = x32.astype(np.float64), y32.astype(np.float64)
+    vx, vy = np.zeros(n), np.zeros(n)
+    res = orc.force_step(x, y, vx, vy, isp, 1 / 240, amb_tol=1e-4, want_forces=True)
+    ok = ~res["amb"]
+    got = np.array([[p.x, p.y] for p in ps], np.float64)
+    ext = np.hypot(x32 - x32.mean(), y32 - y32.mean()).max()
+    # the result is rounded to float32 ABSOLUTE coordinates (ulp 3e-5 at 400), like the reference's own buffers
+    assert np.hypot(got[ok, 0] - x[ok], got[ok, 1] - y[ok]).max() / ext <= 2e-6
+    f_dev = np.array([[p.vx, p.vy] for p in ps], np.float64) / (0.85 / 240)
+    fx, fy = res["fx"], res["fy"]
+    num = np.hypot(f_dev[ok, 0] - fx[ok], f_dev[ok, 1] - fy[ok])
+    assert np.sqrt((num ** 2).sum() / (fx[ok] ** 2 + fy[ok] ** 2).sum()) <= 2e-5
