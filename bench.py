@@ -449,6 +449,7 @@ def main():
     props = (C.c_int64 * 8)()
     lib.pyqmd_device_props(local_rank, props)
     ctx.fp32_peak = max(f1.value, f2.value)
+    ctx.sms, ctx.sm_hz = int(props[0]), float(props[3]) * 1e3
     ctx.peak_info = (f1.value, f2.value, props[0] * 128 * 2 * props[3] * 1e3 / 1e12)
     peaks = {}
     try:
@@ -555,6 +556,17 @@ def cpu_baseline(workload, short=False):
 
 
 # ---------------------------------------------------------------------------------------------
+def mufu_roofline(ctx, evaluations_per_s, mufu_per_evaluation, what):
+    """The pipe that really bounds the force kernels: special-function (MUFU) results, 16 per clock and
+    SM; `frac` = MUFU operations the executed pair evaluations need / that peak."""
+    peak = 16.0 * ctx.sms * ctx.sm_hz
+    need = evaluations_per_s * mufu_per_evaluation
+    return {"mufu_per_executed_evaluation": mufu_per_evaluation, "what": what, "achieved_per_s": need,
+            "peak_per_s": peak, "frac": need / peak,
+            "peak_source": "16 MUFU results per clock and SM (measured 15.9, scripts/ubench/pipes.cu) x %d SMs x "
+                           "%.0f MHz" % (ctx.sms, ctx.sm_hz / 1e6)}
+
+
 def bench_cloud(ctx, workload, K, W, with_e2e=True):
     """C4: one cloud of N nucleons, strong scaling."""
     from pyqmd_b200.forces import NuclearForces
@@ -590,6 +602,8 @@ def bench_cloud(ctx, workload, K, W, with_e2e=True):
                      "kernel": kernel, "flops_per_pair": flops_pair,
                      "algorithmic_bytes_per_launch": 36 * n,
                      "executed_pair_evaluations_per_step": pairs / 2 if sym else pairs,
+                     "mufu": mufu_roofline(ctx, cloud.pairs_per_step() * (0.5 if sym else 1.0) * K / sec, 2.0,
+                                           "far pair: rsqrt + ex2"),
                      "note": ("algorithmic FLOPs of all N(N-1) ordered pairs (SURVEY 8d) over the kernel time; "
                               "the symmetric scheme evaluates each unordered pair once, so `frac` may exceed 1 "
                               "and `frac_executed` (half) is the pipe utilisation; the kernel's own bound is "
@@ -699,6 +713,9 @@ def _ensemble_result(ctx, workload, ens, K, sec, clocks, flops_pair, census, sub
                      and not ctx.args.nuclei and substeps == 1 else None,
                      "kernel": "ensemble kernel (see DESIGN.md section 4)", "flops_per_pair": flops_pair,
                      "algorithmic_bytes_per_launch": 36 * nucleons, "branch_census_end": census,
+                     "mufu": mufu_roofline(ctx, my_rate / 2, 5.0,
+                                           "general law: rsqrt, sqrt, rcp, 2 x ex2 per unordered pair "
+                                           "(idle lanes of partly filled warps not counted)"),
                      "peak_source": "FFMA-chain microbenchmark in this run (scalar %.1f, "
                                     "f32x2 %.1f TFLOP/s); nominal %.1f" % ctx.peak_info,
                      "hbm_gbs": nucleons * 36 * K / sec / 1e9, "hbm_peak_gbs": ctx.hbm_peak,
