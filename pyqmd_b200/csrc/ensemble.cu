@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -880,6 +882,251 @@ static int pick_block_threads(int cap, int* G_out)
     return best_T;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// ensemble_cluster_kernel: ONE nucleus on a thread-block CLUSTER of 8 CTAs (8 SMs), for launches of a
+// handful of nuclei (BASELINE config 1: a single U-238; the interactive app).  Such a launch cannot
+// fill the GPU, its sub-steps are a latency chain -- 21 us each in one CTA -- so the chain is cut
+// eight ways instead:
+//   * every CTA keeps a full replica of the positions and types in its shared memory (double
+//     buffered: Jacobi) and OWNS cnt/8 nucleons; a thread evaluates its nucleon against one slice of
+//     all partners (ordered pairs: with 8 SMs on the job the reaction exchange of Newton's third law
+//     would cost more than it saves), the slices' partial forces meet in shared memory;
+//   * the owner integrates and stores the new position straight into all eight replicas through
+//     distributed shared memory (cluster.map_shared_rank), together with its share of the coordinate
+//     sums and -- CTA 0 -- next sub-step's decay decision; ONE cluster barrier per sub-step;
+//   * a decay (rare) gathers the velocities in CTA 0, whose leader thread runs the serial
+//     transmutation (leader_decay), and redistributes the state.
+constexpr int kClusterSize = 8;
+constexpr int kClusterThreads = 256;
+
+struct ClusterSmem {
+    float* X[2];
+    float* Y[2];
+    float* Tt;          // [capP] types
+    float2* part;       // [slices][ipc] partial forces
+    float2* csum[2];    // [8] per-CTA coordinate sums, per buffer
+    float4* spc;        // [capP] canonical staging (CTA 0 holds the authoritative copy during a decay)
+    float2* sv;         // [capP]
+    int* flags;         // [0..1] fire flag per buffer parity, [2] cnt
+};
+
+__device__ __forceinline__ ClusterSmem carve_cluster(unsigned char* raw, int capP, int slices, int ipc)
+{
+    ClusterSmem S;
+    float* f = reinterpret_cast<float*>(raw);
+    S.X[0] = f; S.X[1] = f + capP; S.Y[0] = f + 2 * capP; S.Y[1] = f + 3 * capP; S.Tt = f + 4 * capP;
+    S.spc = reinterpret_cast<float4*>(f + 5 * capP + (capP & 3 ? 4 - (capP & 3) : 0));
+    S.sv = reinterpret_cast<float2*>(S.spc + capP);
+    S.part = S.sv + capP;
+    S.csum[0] = S.part + slices * ipc;
+    S.csum[1] = S.csum[0] + kClusterSize;
+    S.flags = reinterpret_cast<int*>(S.csum[1] + kClusterSize);
+    return S;
+}
+
+static size_t cluster_smem_bytes(int capP, int slices, int ipc)
+{
+    return sizeof(float) * (5 * (size_t)capP + 4) + sizeof(float4) * capP + sizeof(float2) * capP +
+           sizeof(float2) * ((size_t)slices * ipc + 2 * kClusterSize) + sizeof(int) * 4 + 32;
+}
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClusterThreads, 1)
+ensemble_cluster_kernel(const pyqmd_ensemble e, const LawParams L, const int n_steps, const int capP,
+                        const int ipc)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int slices = kClusterThreads / ipc;
+    const ClusterSmem S = carve_cluster(smem_raw, capP, slices, ipc);
+    // the same address in CTA r of the cluster (distributed shared memory)
+    auto remote = [&](auto* ptr, int r) { return cluster.map_shared_rank(ptr, r); };
+
+    const int c = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x / kClusterSize;            // one cluster per listed nucleus
+    const int nuc = e.list ? e.list[q] : (int)q;
+    const int64_t off = e.offset[nuc];
+    int cnt = e.count[nuc];
+    const int il = tid % ipc, sl = tid / ipc;
+    const bool leader = (c == 0 && tid == 0);
+
+    // layout derived from the live count
+    int per, i, jper, j0, j1;
+    bool owner;
+    auto layout = [&]() {
+        per = (cnt + kClusterSize - 1) / kClusterSize;      // nucleons per CTA (<= ipc)
+        i = c * per + il;
+        owner = (sl == 0) && il < per && i < cnt;
+        jper = (((cnt + slices - 1) / slices) + 1) & ~1;    // partners per slice, even (packed pairs)
+        j0 = sl * jper;
+        j1 = min(j0 + jper, (cnt + 1) & ~1);
+    };
+    layout();
+
+    // replicas: every CTA loads the whole nucleus; velocities stay with the owners
+    for (int k = tid; k < capP; k += kClusterThreads) {
+        float x = kGhost, y = kGhost, t = 0.f;
+        if (k < cnt) {
+            const float2 p2 = reinterpret_cast<const float2*>(e.pos)[off + k];
+            x = p2.x; y = p2.y;
+            t = e.is_proton[off + k] ? 1.0f : 0.0f;
+        }
+        S.X[0][k] = x; S.Y[0][k] = y; S.Tt[k] = t;
+        S.X[1][k] = kGhost; S.Y[1][k] = kGhost;
+    }
+    float2 vel = make_float2(0.f, 0.f);
+    if (owner) vel = reinterpret_cast<const float2*>(e.vel)[off + i];
+    __syncthreads();
+    // this CTA's share of the coordinate sums of buffer 0, published to every CTA
+    auto publish_sum = [&](int buf) {
+        if (tid < 32) {
+            float sx = 0.f, sy = 0.f;
+            for (int k = c * per + tid; k < min((c + 1) * per, cnt); k += 32) { sx += S.X[buf][k]; sy += S.Y[buf][k]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            }
+            if (tid < kClusterSize) remote(S.csum[buf], tid)[c] = make_float2(sx, sy);
+        }
+    };
+    publish_sum(0);
+
+    int32_t zn = 0;
+    double T_half = 0.0, p_dec = -1.0;
+    if (leader && e.decay_enabled) {
+        zn = e.zn[nuc];
+        T_half = e.half_life[nuc];
+        p_dec = e.p_decay[nuc];
+    }
+    const DrawSource draws{e.uniforms, e.seed, e.uniforms_n};
+    const GenConsts gc = make_gen_consts(L);
+    // decay decision of sub-step `s` (Nucleus.should_decay, particles.py:126-147): taken by the leader and
+    // stored in every CTA one cluster barrier ahead of its use
+    auto decide = [&](int s, int parity) {
+        bool fire = false;
+        if (e.decay_enabled && p_dec >= 0.0 && s < n_steps) {      // stable: no draw (:129-130)
+            const double u0 = draws.one((uint64_t)(e.id_base + nuc), nuc, e.step0 + (uint32_t)s, s, 0);
+            fire = u0 < p_dec;                                      // :147
+        }
+#pragma unroll
+        for (int r = 0; r < kClusterSize; ++r) remote(S.flags, r)[parity] = fire ? 1 : 0;
+    };
+    if (leader) decide(0, 0);
+    cluster.sync();
+
+    int buf = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        if (e.decay_enabled && S.flags[s & 1]) {
+            // ---- decay: physics slice of handle_decay, nuclear_sim.py:213,288-294,349,353 -----------
+            if (owner) remote(S.sv, 0)[i] = vel;            // velocities to CTA 0 (canonical order)
+            cluster.sync();
+            if (c == 0) {
+                for (int k = tid; k < cnt; k += kClusterThreads)
+                    S.spc[k] = make_float4(S.X[buf][k], S.Y[buf][k], S.Tt[k], 0.f);
+                __syncthreads();
+                if (tid == 0) {
+                    leader_decay(e, draws, S.spc, S.sv, 0, cnt, nuc, e.step0 + (uint32_t)s, s, zn, T_half, p_dec);
+#pragma unroll
+                    for (int r = 0; r < kClusterSize; ++r) remote(S.flags, r)[2] = cnt;
+                }
+            }
+            cluster.sync();
+            cnt = S.flags[2];
+            layout();
+            const float4* spc0 = remote(S.spc, 0);
+            for (int k = tid; k < capP; k += kClusterThreads) {      // every CTA pulls the new state
+                float4 a = make_float4(kGhost, kGhost, 0.f, 0.f);
+                if (k < cnt) a = spc0[k];
+                S.X[buf][k] = a.x; S.Y[buf][k] = a.y; S.Tt[k] = a.z;
+                S.X[buf ^ 1][k] = kGhost; S.Y[buf ^ 1][k] = kGhost;    // no stale nucleon beyond the new count
+            }
+            vel = make_float2(0.f, 0.f);
+            if (owner) vel = remote(S.sv, 0)[i];
+            __syncthreads();
+            publish_sum(buf);
+            cluster.sync();                                  // CTA 0's staging consumed; sums in place
+        }
+
+        // ---- centre of mass, nuclear_forces.py:242-243 ------------------------------------------------
+        float cx, cy;
+        if (e.centre) {
+            cx = e.centre[2 * (int64_t)nuc];
+            cy = e.centre[2 * (int64_t)nuc + 1];
+        } else {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int r = 0; r < kClusterSize; ++r) { sx += S.csum[buf][r].x; sy += S.csum[buf][r].y; }
+            const float inv_n = 1.0f / (float)max(cnt, 1);
+            cx = sx * inv_n; cy = sy * inv_n;
+        }
+        // ---- pair forces of nucleon i against the partners of slice sl, :248-298 ----------------------
+        const bool has_i = il < per && i < cnt;
+        const float xi = has_i ? S.X[buf][i] : kGhost, yi = has_i ? S.Y[buf][i] : kGhost;
+        const float ti = has_i ? S.Tt[i] : 0.f;
+        const f32x2 xi2 = pk1(xi), yi2 = pk1(yi), ti2 = pk1(ti), negC = pk1(-L.C);
+        f32x2 fx2 = 0ull, fy2 = 0ull;
+        const float2* X2 = reinterpret_cast<const float2*>(S.X[buf]);
+        const float2* Y2 = reinterpret_cast<const float2*>(S.Y[buf]);
+        const float2* T2 = reinterpret_cast<const float2*>(S.Tt);
+#pragma unroll 2
+        for (int j = j0; j < j1; j += 2) {                  // the self pair is skipped by d2 < 0.01 (:257)
+            const float2 xj = X2[j >> 1], yj = Y2[j >> 1], tj = T2[j >> 1];
+            const f32x2 dx = sub2(pk(xj.x, xj.y), xi2), dy = sub2(pk(yj.x, yj.y), yi2);
+            const f32x2 sc = pair_general2(dx, dy, tj.x, tj.y, ti, ti2, mul2(negC, pk(tj.x, tj.y)), gc, L);
+            fx2 = fma2(dx, sc, fx2);
+            fy2 = fma2(dy, sc, fy2);
+        }
+        {
+            float a, b, c2, d;
+            upk(fx2, a, b);
+            upk(fy2, c2, d);
+            S.part[sl * ipc + il] = make_float2(a + b, c2 + d);
+        }
+        __syncthreads();
+        const int nb = buf ^ 1;
+        if (owner) {
+            float fx = 0.f, fy = 0.f;
+            for (int k = 0; k < slices; ++k) {              // fixed order: reproducible
+                const float2 pf = S.part[k * ipc + il];
+                fx += pf.x; fy += pf.y;
+            }
+            float x = xi, y = yi;
+            const float Rn = 2.4f * cbrtf((float)cnt);      // nuclear_forces.py:304
+            contain_and_integrate(x, y, vel.x, vel.y, fx, fy, cx, cy, Rn, e.dt_phys);   // :301-323
+            if (e.force && s == n_steps - 1) reinterpret_cast<float2*>(e.force)[off + i] = make_float2(fx, fy);
+#pragma unroll
+            for (int r = 0; r < kClusterSize; ++r) {        // the new position into every replica
+                remote(S.X[nb], r)[i] = x;
+                remote(S.Y[nb], r)[i] = y;
+            }
+            S.X[nb][i] = x; S.Y[nb][i] = y;                 // (own replica: visible below after __syncthreads)
+        }
+        __syncthreads();                                    // this CTA's new positions are in its own replica
+        publish_sum(nb);
+        if (leader) decide(s + 1, (s + 1) & 1);
+        cluster.sync();                                     // Jacobi: every replica complete before the next read
+        buf = nb;
+    }
+
+    if (owner) {
+        reinterpret_cast<float2*>(e.pos)[off + i] = make_float2(S.X[buf][i], S.Y[buf][i]);
+        reinterpret_cast<float2*>(e.vel)[off + i] = vel;
+        if (e.decay_enabled) e.is_proton[off + i] = (S.Tt[i] != 0.f) ? 1 : 0;
+    }
+    if (leader) {
+        e.count[nuc] = cnt;
+        if (e.decay_enabled) {
+            e.zn[nuc] = zn;
+            e.half_life[nuc] = T_half;
+            e.p_decay[nuc] = p_dec;
+        }
+    }
+    cluster.sync();                                         // nobody leaves while peers may still address its memory
+}
+
 }  // namespace pyqmd
 
 using namespace pyqmd;
@@ -935,6 +1182,24 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
     // 26 of 32 lanes) loses more than that; the block-wide ring packs G nuclei into one block instead.
     // Measured on B200 (r02, pairs/s, ring vs block): U-238 1.21e12 / 1.10e12, Pb-208 1.05 / 1.15,
     // Au-197 0.98 / 1.08, Ag-107 1.02 / 1.05, Fe-56 0.85 / 0.75, C-14 0.36 / 0.31.
+    // a handful of heavy nuclei: one nucleus per 8-CTA cluster (latency path)
+    {
+        const char* force = getenv("PYQMD_ENSEMBLE_KERNEL");
+        const bool eligible = e->cap >= 64 && e->cap <= 512;
+        // 8 SMs per nucleus, twice the pair evaluations (ordered pairs): 3.4 us per U-238 sub-step against
+        // 21 us in one CTA, so it pays while the clusters run in at most ~4 waves (16-18 clusters fit at once)
+        const bool want = force ? !strcmp(force, "cluster") : (n_list <= 64);
+        if (eligible && want) {
+            const int capP = (e->cap + 3) & ~3;
+            const int ipc = e->cap <= 256 ? 32 : 64;
+            const size_t sm = cluster_smem_bytes(capP, kClusterThreads / ipc, ipc);
+            PYQMD_REQUIRE(n_list <= 2147483647LL / kClusterSize, "too many nuclei for one launch");
+            ensemble_cluster_kernel<<<(unsigned)(n_list * kClusterSize), kClusterThreads, sm, st>>>(
+                d, L, n_steps, capP, ipc);
+            PYQMD_CUDA_CHECK(cudaGetLastError());
+            return PYQMD_OK;
+        }
+    }
     bool use_ring = true;
     if (e->cap > 64 && e->cap <= 512) {
         const int S = (e->cap + kQ - 1) / kQ;
@@ -944,8 +1209,9 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
         const int Tp = pick_block_threads(capT, &Gp);
         const double u_block = (double)Gp * capT / Tp;
         use_ring = u_ring >= 0.92 * u_block || pair_smem_bytes(Tp, Gp, capT) > 200 * 1024;
-        // a handful of nuclei cannot fill the GPU: the step is a latency chain, and the block ring puts
-        // twice as many threads on a nucleus (one U-238 alone: 18.7 us per sub-step against 26.8 us)
+        // a few hundred nuclei cannot fill the GPU: the step is a latency chain, and the block ring puts
+        // twice as many threads on a nucleus (one U-238 alone: 21 us per sub-step against 27 us); below
+        // 64 nuclei the cluster kernel above has already taken the launch
         int dev = 0, sms = 0;
         PYQMD_CUDA_CHECK(cudaGetDevice(&dev));
         PYQMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

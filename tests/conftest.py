@@ -63,10 +63,11 @@ def u238_traj():
     return dict(np.load(os.path.join(GOLD, "u238_traj.npz")))
 
 
-@pytest.fixture(params=["ring", "block"])
+@pytest.fixture(params=["ring", "block", "cluster"])
 def ensemble_kernel(request, monkeypatch):
-    """Pins pyqmd_ensemble_step's choice between the warp-local ring kernel and the block-wide ring
-    (csrc/ensemble.cu) so that BOTH see the parity case, whatever the automatic dispatch would pick for
-    its size (small test ensembles would otherwise always take the low-latency block ring)."""
+    """Pins pyqmd_ensemble_step's choice between the warp-local ring kernel, the block-wide ring and the
+    8-CTA cluster kernel (csrc/ensemble.cu) so that ALL of them see the parity case, whatever the automatic
+    dispatch would pick for its size ("cluster" applies to nuclei of 64..512 nucleons, others take the
+    automatic choice)."""
     monkeypatch.setenv("PYQMD_ENSEMBLE_KERNEL", request.param)
     return request.param
