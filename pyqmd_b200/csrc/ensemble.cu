@@ -897,8 +897,11 @@ static int pick_block_threads(int cap, int* G_out)
 //     sums and -- CTA 0 -- next sub-step's decay decision; ONE cluster barrier per sub-step;
 //   * a decay (rare) gathers the velocities in CTA 0, whose leader thread runs the serial
 //     transmutation (leader_decay), and redistributes the state.
+#ifndef PYQMD_CLUSTER_THREADS
+#define PYQMD_CLUSTER_THREADS 256
+#endif
 constexpr int kClusterSize = 8;
-constexpr int kClusterThreads = 256;
+constexpr int kClusterThreads = PYQMD_CLUSTER_THREADS;
 
 struct ClusterSmem {
     float* X[2];
