@@ -82,7 +82,7 @@ __device__ __forceinline__ uint64_t cloud_sort_key(float2 p, bool proton, float 
 }
 
 struct FarConsts {
-    f32x2 kexp, logA, l1, l2, g1, g2, one, negC;
+    f32x2 kexp, logA, l1, l2, g1, g2, one, negC, cg1, cg2;
 };
 
 // Far-field approximations (all inside the 1e-5 budget, errors relative to the exact term):
@@ -105,36 +105,52 @@ __device__ __forceinline__ FarConsts make_far_consts(const LawParams& L)
     c.g2 = pk1(kG2);
     c.one = pk1(1.0f);
     c.negC = pk1(-L.C);
+    c.cg1 = pk1(-L.C * kG1);
+    c.cg2 = pk1(-L.C * kG2);
     return c;
 }
 
-// Two far pairs (one i, two j) in packed form.
-//   s = net / d,  net = 0.15 S exp(-1.8 d/7)/(d + eps) - [pp] C/(d2 + eps)      [281,285]
-// FMA-pipe operations per pair: 12 (MODE 0), 15 (MODE 1), 17 (MODE 2); special-function ops: 2
-// (rsqrt, ex2).  A degree-5 polynomial 2^x on the FMA pipe for a share of the pairs was measured
-// (r01e+) and rejected: every share was slower, the FMA pipe is as busy as the XU pipe.
+// s = net / d of two far pairs (packed), given d2 = dx^2 + dy^2 >= 81:
+//   net = 0.15 S exp(-1.8 d/7)/(d + eps) - [pp] C/(d2 + eps)                     [281,285]
+// With r = rsqrt(d2) the exponent of the tail is  logA + k d + r (l1 + l2 r) = logA + r (k d2 + l1 + l2 r)
+// -- k d2 + l1 does not wait for the rsqrt -- and the Coulomb term of an all-proton tile pair is
+// r2 r G(r2), G = -C g(r2) with the charge folded into the polynomial's coefficients.
+// FMA-pipe operations per pair besides dx, dy, d2 and the force accumulation: 5 (MODE 0), 8 (MODE 1),
+// 10 (MODE 2; cq = -C t_i t_j comes from the caller); special-function operations: 2 (rsqrt, ex2).
+// NOEXP (MODE 1 / 2 only): the caller has proved that the tail term is exactly zero (cloud_sym.cu,
+// kUltraGap), so e = +0 enters the same expression: identical bits without the exponential.
+// A degree-5 polynomial 2^x on the FMA pipe for a share of the pairs was measured (r01e+) and
+// rejected: every share was slower, the FMA pipe is as busy as the XU pipe.
+template <int MODE, bool NOEXP = false>
+__device__ __forceinline__ f32x2 far_s2(f32x2 d2, f32x2 cq, const FarConsts& c)
+{
+    float a0, a1;
+    upk(d2, a0, a1);
+    const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
+    f32x2 e = 0ull;
+    if (!NOEXP) {
+        const f32x2 u = fma2(d2, c.kexp, c.l1);
+        const f32x2 arg = fma2(r, fma2(r, c.l2, u), c.logA);
+        upk(arg, a0, a1);
+        e = pk(mufu_ex2(a0), mufu_ex2(a1));
+    }
+    const f32x2 r2 = mul2(r, r);
+    if (MODE == 0) return mul2(e, r2);
+    if (MODE == 1) {
+        const f32x2 G = fma2(r2, fma2(r2, c.cg2, c.cg1), c.negC);     // -C d2/(d2+eps)
+        return mul2(r2, fma2(G, r, e));
+    }
+    const f32x2 g = fma2(r2, fma2(r2, c.g2, c.g1), c.one);            // d2/(d2+eps)
+    return mul2(r2, fma2(mul2(cq, r), g, e));                         // cq carries the minus sign
+}
+
+// Two far pairs (one i, two j) in packed form: action on i.
 template <int MODE>
 __device__ __forceinline__ void far_pair2(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
                                           const FarConsts& c, f32x2& fx, f32x2& fy)
 {
     const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
-    const f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
-    float a0, a1;
-    upk(d2, a0, a1);
-    const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
-    f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
-    arg = fma2(r, fma2(r, c.l2, c.l1), arg);
-    upk(arg, a0, a1);
-    const f32x2 e = pk(mufu_ex2(a0), mufu_ex2(a1));
-    const f32x2 r2 = mul2(r, r);
-    f32x2 s;
-    if (MODE == 0) {
-        s = mul2(e, r2);
-    } else {
-        const f32x2 g = fma2(r2, fma2(r2, c.g2, c.g1), c.one);        // (d2)/(d2+eps)
-        const f32x2 q = (MODE == 1) ? c.negC : cq;                    // cq already carries the minus sign
-        s = mul2(r2, fma2(mul2(q, r), g, e));
-    }
+    const f32x2 s = far_s2<MODE>(fma2(dy, dy, mul2(dx, dx)), cq, c);
     fx = fma2(dx, s, fx);
     fy = fma2(dy, s, fy);
 }

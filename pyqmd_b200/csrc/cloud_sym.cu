@@ -7,7 +7,7 @@
 // and FMA work disappears.  BASELINE config 4 (N = 1M).
 //
 // Decomposition
-//   * i-blocks ("rows") of 1024 nucleons, j-tiles of 256.  Row b owns the tiles t >= 4b: its own
+//   * i-blocks ("rows") of kSymIBlock = 1024 nucleons, j-tiles of 256.  Row b owns the tiles t >= 4b: its own
 //     4 diagonal tiles (ordered evaluation, no reaction) and every tile after them (each pair once,
 //     reaction on j).  A work unit is (row, run of tiles_per_unit tiles); rows are dealt to the
 //     `n_parts` GPUs boustrophedon-wise so the triangular work is balanced.
@@ -28,12 +28,24 @@
 namespace pyqmd {
 
 #ifndef PYQMD_SYM_UNROLL
-#define PYQMD_SYM_UNROLL 1
+#define PYQMD_SYM_UNROLL 2
+#endif
+#ifndef PYQMD_SYM_THREADS
+#define PYQMD_SYM_THREADS 256
 #endif
 constexpr int kSymUnroll = PYQMD_SYM_UNROLL;
+#ifndef PYQMD_SYM_MINBLOCKS
+#define PYQMD_SYM_MINBLOCKS 2
+#endif
 constexpr float kGhostI = -3.0e18f;   // padding i-nucleons: every term of the law is exactly 0
 constexpr float kGhostJ = 3.0e18f;    // padding j-nucleons (distinct from the i ghosts: d2 finite, > 0)
-constexpr int kWarps = kThreads / 32;
+// 256 threads x 2 blocks per SM = 16 warps at 128 registers.  Measured on B200 at N = 1M (round 2): 320
+// threads x 2 = 20 warps at 96 registers is 10 % slower although its spills sit outside the sweep loops,
+// one block of 256 at 252 registers (8 warps) 14 % slower: the sweep wants both the registers and the warps.
+constexpr int kSymThreads = PYQMD_SYM_THREADS;
+constexpr int kWarps = kSymThreads / 32;
+constexpr int kSymIBlock = kSymThreads * kIPT;
+static_assert(kSymThreads >= kTile && kSymIBlock % kTile == 0, "rows are whole tiles; one j per fetching thread");
 constexpr int kHalf = 128;            // j-nucleons per 32-step sweep (32 lanes x 4)
 
 struct SymParams {
@@ -47,41 +59,21 @@ struct SymParams {
 };
 
 // Beyond this bounding-box gap the tail term 0.15 S exp(-1.8 d / 7) / (d + eps) is EXACTLY zero in the
-// arithmetic of far_pair2_sym: its exponent argument log2(0.15 S) - 0.371 d (+ a correction < 1e-3) is
+// arithmetic of far_s2: its exponent argument log2(0.15 S) - 0.371 d (+ a correction < 1e-3) is
 // below -126, and ex2.approx.ftz flushes 2^x to +0 there.  What is left of such a pair is the Coulomb
 // term (p-p only).  d >= 353 covers every S <= 180 (log2(0.15 S) <= 4.76); the host checks the bound and
 // ignores the flag otherwise.
 constexpr float kUltraGap = 353.0f;
 
-// Two far pairs (one i, two j), action on i and (REACT) reaction on the two j.
-// NOEXP (MODE 1 / 2 only): the caller has proved that the tail term is exactly zero (kUltraGap), so
-// s = r2 ((q r) g + 0): the same bits as the full expression, without its exponential.
+// Two far pairs (one i, two j), action on i and (REACT) reaction on the two j; far_s2 (cloud.cuh) is
+// the law.  NOEXP (MODE 1 / 2 only): the tail term of every pair of the tile is exactly zero (kUltraGap).
 template <int MODE, bool REACT, bool NOEXP = false>
 __device__ __forceinline__ void far_pair2_sym(f32x2 xj, f32x2 yj, f32x2 xi, f32x2 yi, f32x2 cq,
                                               const FarConsts& c, f32x2& fx, f32x2& fy, f32x2& rx,
                                               f32x2& ry)
 {
     const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
-    const f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
-    float a0, a1;
-    upk(d2, a0, a1);
-    const f32x2 r = pk(mufu_rsqrt(a0), mufu_rsqrt(a1));
-    f32x2 e = 0ull;
-    if (!NOEXP) {
-        f32x2 arg = fma2(mul2(d2, r), c.kexp, c.logA);
-        arg = fma2(r, fma2(r, c.l2, c.l1), arg);
-        upk(arg, a0, a1);
-        e = pk(mufu_ex2(a0), mufu_ex2(a1));
-    }
-    const f32x2 r2 = mul2(r, r);
-    f32x2 s;
-    if (MODE == 0) {
-        s = mul2(e, r2);
-    } else {
-        const f32x2 g = fma2(r2, fma2(r2, c.g2, c.g1), c.one);
-        const f32x2 q = (MODE == 1) ? c.negC : cq;
-        s = mul2(r2, fma2(mul2(q, r), g, e));
-    }
+    const f32x2 s = far_s2<MODE, NOEXP>(fma2(dy, dy, mul2(dx, dx)), cq, c);
     fx = fma2(dx, s, fx);
     fy = fma2(dy, s, fy);
     if (REACT) {
@@ -231,7 +223,7 @@ __device__ __forceinline__ void acc_add(long long* acc, int64_t i, double fx, do
               (unsigned long long)__double2ll_rn(fy * (double)scale));
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kSymThreads, PYQMD_SYM_MINBLOCKS)
 cloud_sym_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp, SymParams sp,
                  CloudWorkspace w, LawParams L, long long* __restrict__ acc)
 {
@@ -244,14 +236,14 @@ cloud_sym_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp
     const int g = blockIdx.y;
     const int b = g * sp.n_parts + ((g & 1) ? sp.n_parts - 1 - sp.part : sp.part);
     if (b >= sp.nb) return;
-    const int first = b * (kIBlock / kTile);
+    const int first = b * (kSymIBlock / kTile);
     const int t_begin = first + (int)blockIdx.x * sp.tiles_per_unit;
     if (t_begin >= sp.nt) return;
     const int t_end = min(t_begin + sp.tiles_per_unit, sp.nt);
     const int64_t n = sp.n;
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t wbase = (int64_t)b * kIBlock + (int64_t)wid * (32 * kIPT);
+    const int64_t wbase = (int64_t)b * kSymIBlock + (int64_t)wid * (32 * kIPT);
     float xi[kIPT], yi[kIPT], ti[kIPT], fx[kIPT], fy[kIPT];
     double Fx[kIPT], Fy[kIPT];
     float bxmin = INFINITY, bymin = INFINITY, bxmax = -INFINITY, bymax = -INFINITY;
@@ -283,21 +275,25 @@ cloud_sym_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp
     alln = __all_sync(0xffffffffu, alln);
 
     // software pipeline of the j tiles (register prefetch -> the other shared-memory buffer)
+    const bool loader = threadIdx.x < kTile;              // one j of the tile per loading thread
     float2 nxt = make_float2(kGhostJ, kGhostJ);
     float nxt_t = 0.f;
     auto fetch = [&](int tile) {
         nxt = make_float2(kGhostJ, kGhostJ);
         nxt_t = 0.f;
         const int64_t j = (int64_t)tile * kTile + threadIdx.x;
-        if (tile < t_end && j < n) { nxt = pos[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
+        if (loader && tile < t_end && j < n) { nxt = pos[j]; nxt_t = isp[j] ? 1.0f : 0.0f; }
     };
     fetch(t_begin);
-    sxb[0][threadIdx.x] = nxt.x;
-    syb[0][threadIdx.x] = nxt.y;
-    stb[0][threadIdx.x] = nxt_t;
+    if (loader) {
+        sxb[0][threadIdx.x] = nxt.x;
+        syb[0][threadIdx.x] = nxt.y;
+        stb[0][threadIdx.x] = nxt_t;
+    }
     fetch(t_begin + 1);
 
-    auto flush = [&](int rb, int tile) {                  // reaction of `tile`: 8 warp rows -> accumulators
+    auto flush = [&](int rb, int tile) {                  // reaction of `tile`: the warps' rows -> accumulators
+        if (!loader) return;
         float sx = 0.f, sy = 0.f;
 #pragma unroll
         for (int k = 0; k < kWarps; ++k) {                // fixed order
@@ -315,12 +311,14 @@ cloud_sym_kernel(const float2* __restrict__ pos, const uint8_t* __restrict__ isp
         __syncthreads();          // tile data complete in `buf`; everybody is done with tile - 1
         if (prev_react) flush(buf ^ 1, tile - 1);
         if (tile + 1 < t_end) {
-            sxb[buf ^ 1][threadIdx.x] = nxt.x;
-            syb[buf ^ 1][threadIdx.x] = nxt.y;
-            stb[buf ^ 1][threadIdx.x] = nxt_t;
+            if (loader) {
+                sxb[buf ^ 1][threadIdx.x] = nxt.x;
+                syb[buf ^ 1][threadIdx.x] = nxt.y;
+                stb[buf ^ 1][threadIdx.x] = nxt_t;
+            }
             fetch(tile + 2);
         }
-        const bool diag = tile < first + kIBlock / kTile;
+        const bool diag = tile < first + kSymIBlock / kTile;
         const float4 bb = w.bbox[tile];
         const int tf = w.flags[tile];
         const float gx = fmaxf(0.f, fmaxf(bb.x - bxmax, bxmin - bb.z));
@@ -463,7 +461,7 @@ extern "C" int pyqmd_cloud_pair_forces_ex(const float* pos, const uint8_t* is_pr
     const LawParams L = make_law_params(strong, coulomb, pauli);
     SymParams sp;
     sp.n = n;
-    sp.nb = (int)((n + kIBlock - 1) / kIBlock);
+    sp.nb = (int)((n + kSymIBlock - 1) / kSymIBlock);
     sp.nt = (int)nt;
     sp.part = part;
     sp.n_parts = n_parts;
@@ -485,7 +483,7 @@ extern "C" int pyqmd_cloud_pair_forces_ex(const float* pos, const uint8_t* is_pr
     const int units_max = (int)((nt + tpu - 1) / tpu);
     PYQMD_REQUIRE(rows_mine <= 65535, "too many rows for one launch");
     const dim3 grid((unsigned)units_max, (unsigned)rows_mine);
-    cloud_sym_kernel<<<grid, kThreads, 0, st>>>(reinterpret_cast<const float2*>(pos), is_proton, sp, w,
+    cloud_sym_kernel<<<grid, kSymThreads, 0, st>>>(reinterpret_cast<const float2*>(pos), is_proton, sp, w,
                                                 L, force_acc);
     PYQMD_CUDA_CHECK(cudaGetLastError());
     return PYQMD_OK;

@@ -122,7 +122,7 @@ __device__ __forceinline__ float pair_general(float dx, float dy, float ti, floa
     const float d = d2 * rinv;                                    // [260]
 
     // hard core: -60 * ((4.25-d)/4.25)^1.5 for d < 4.25           [264-267]
-    const float ov = fmaxf(fmaf(d, -1.0f / kHardD, 1.0f), 0.0f);
+    const float ov = __saturatef(fmaf(d, -1.0f / kHardD, 1.0f));
     float net = -60.0f * ov * mufu_sqrt(ov);
 
     // strong force: one reciprocal serves 1/(d+eps) and 1/(d2+eps) [275,278,281,285]
@@ -192,10 +192,12 @@ __device__ __forceinline__ f32x2 pair_general2(f32x2 dx, f32x2 dy, float ta, flo
     const f32x2 rinv = pk(mufu_rsqrt(d2a), mufu_rsqrt(d2b));
     const f32x2 d = mul2(d2, rinv);                                 // [260]
     // hard core                                                     [264-267]
-    float ova, ovb;
-    upk(fma2(d, c.nInvHard, c.one), ova, ovb);
-    ova = fmaxf(ova, 0.f);
-    ovb = fmaxf(ovb, 0.f);
+    // 1 - d/4.25 clamped at 0 is a saturating FMA (d >= 0, so the upper bound 1 never binds; a NaN d
+    // of a self pair saturates to 0): two scalar FFMA.SAT instead of FFMA2 + two FMNMX
+    float da, db;
+    upk(d, da, db);
+    const float ova = __saturatef(fmaf(da, -1.0f / kHardD, 1.0f));
+    const float ovb = __saturatef(fmaf(db, -1.0f / kHardD, 1.0f));
     const f32x2 hc = mul2(pk(ova, ovb), pk(mufu_sqrt(ova), mufu_sqrt(ovb)));
     // strong                                                        [273-281]
     const f32x2 a = fma2(d, c.sgn, c.sgnEps), b = add2(d2, c.eps);   // a = sgn(S) (d + eps)
