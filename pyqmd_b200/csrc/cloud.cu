@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(256) cloud_centre(CloudWorkspace w, int64_t n_
 // pairs, so the FMA-pipe operations of a far pair cost half the issue slots and the kernel moves
 // from issue-bound (ncu r01a: 82 % issue, 18 instr/pair) to pipe-bound.  ncu r01e (14 FMA-pipe ops
 // + 2 special-function ops per pair): XU pipe 84 %, FMA pipe ~80 % busy -- both near saturation,
-// so this version trims the FMA work to 12 ops per pair.  (Moving a share of the 2^x evaluations
-// from the XU pipe to an FMA-pipe polynomial was measured and rejected: every share was slower.)
+// so the FMA work was trimmed: now 11 ops per ordered pair without a Coulomb term (dx, dy, d2: 4;
+// far_s2: 5; accumulation: 2).  (Moving a share of the 2^x evaluations from the XU pipe to an FMA-pipe
+// polynomial was measured and rejected: every share was slower.)
 template <int MODE>
 __device__ __forceinline__ void far_tile_packed(const float* __restrict__ sx,
                                                 const float* __restrict__ sy,

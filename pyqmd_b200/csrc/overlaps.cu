@@ -8,6 +8,7 @@
 // parallel, and the pushes of a chunk are applied one at a time in j order (ballot + first set
 // bit), re-testing the remaining lanes against the updated i.  Rows with no overlap cost one
 // ballot per 32 partners.  Positions live in shared memory for the whole sweep.
+#include <mutex>
 #include "common.cuh"
 #include "decay_device.cuh"
 
@@ -162,12 +163,19 @@ extern "C" int pyqmd_resolve_overlaps(const pyqmd_ensemble* e, const double* uni
     const int64_t grid = (n_list + kOvWarps - 1) / kOvWarps;
     PYQMD_REQUIRE(grid <= 2147483647LL, "too many nuclei for one launch");
     const size_t smem = (size_t)kOvWarps * e->cap * sizeof(float2);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(resolve_overlaps_kernel,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              200 * 1024));
-        attr_set = true;
+    if (smem > 48 * 1024) {
+        // cudaFuncSetAttribute is per device: remember which devices have been configured
+        static unsigned char done[64] = {0};
+        static std::mutex mu;
+        int dev = 0;
+        PYQMD_CUDA_CHECK(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            PYQMD_CUDA_CHECK(cudaFuncSetAttribute(resolve_overlaps_kernel,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  200 * 1024));
+            if (dev >= 0 && dev < 64) done[dev] = 1;
+        }
     }
     resolve_overlaps_kernel<<<(unsigned)grid, kOvWarps * 32, smem, (cudaStream_t)stream>>>(
         d, uniforms, uniforms_per_nucleus, n_pushes);
