@@ -13,7 +13,8 @@ Contract (one JSON line from rank 0):
            largest single-GPU config.  "strong" scaling: the cloud is split over the ranks (i-block
            rows of the symmetric scheme dealt to the ranks; per step an integer reduce-scatter of
            the force accumulators + integrate + all-gather of positions, fused into ONE
-           peer-memory kernel over NVLink -- `config.exchange` says which exchange ran)
+           peer-memory kernel over NVLink -- `details.exchange_used` says which exchange ran; if
+           symmetric memory cannot be set up the bench falls back to NCCL collectives and says so)
   value    device-resident throughput (state already in HBM), CUDA events, max over ranks
   e2e      the same metric through the host-buffer API, state in pinned HOST memory, copies inside
            the timed region every step.  1 GPU: NuclearForces.step_cloud -> pyqmd_cloud_step_host
@@ -575,7 +576,7 @@ def bench_cloud(ctx, workload, K, W, with_e2e=True):
     n = args.cloud_n
     pos, isp = make_cloud(n)
     cloud = NucleonCloud(pos, isp, device=ctx.dev, rank=ctx.rank, world=ctx.world, scheme=args.cloud_scheme,
-                         exchange=args.cloud_exchange)
+                         exchange=args.cloud_exchange, allow_nccl_fallback=True)
     sec, clocks = ctx.timed(lambda: cloud.step(1), K, W, flush="inside")
     pairs = float(n) * (n - 1)
     f_pp = (float(isp.sum()) / n) ** 2
@@ -661,9 +662,9 @@ def bench_cloud_skip(ctx, workload, K, W, with_e2e=False):
     n = args.cloud_n
     pos, isp = make_cloud(n)
     cloud = NucleonCloud(pos, isp, device=ctx.dev, rank=ctx.rank, world=ctx.world, scheme="symmetric",
-                         exchange=args.cloud_exchange, skip_exact_zeros=True)
+                         exchange=args.cloud_exchange, allow_nccl_fallback=True, skip_exact_zeros=True)
     check = NucleonCloud(pos, isp, device=ctx.dev, rank=ctx.rank, world=ctx.world, scheme="symmetric",
-                         exchange=args.cloud_exchange)
+                         exchange=args.cloud_exchange, allow_nccl_fallback=True)
     cloud.step(1); check.step(1)
     same = bool(torch.equal(cloud.pos, check.pos) and torch.equal(cloud.vel, check.vel))
     del check
