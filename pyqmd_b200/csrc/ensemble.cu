@@ -884,6 +884,304 @@ static int pick_block_threads(int cap, int* G_out)
 
 
 // ---------------------------------------------------------------------------------------------------
+// ensemble_quad_kernel: the block-wide ring with FOUR nucleons per thread.
+//
+// The warp-local rings above execute ~20 % fewer instructions per pair than ensemble_pair_kernel (16 pairs
+// per visit, no per-pair index arithmetic), but a nucleus whose subgroups do not fill its warps leaves
+// lanes idle (Pb-208: 52 subgroups on 64 lanes).  Here the subgroups of G nuclei are packed into one block
+// -- thread tid owns subgroup tid % capT of nucleus tid / capT, so a warp may span two nuclei and no lane
+// idles but the block's last few -- and the ring runs over the whole nucleus: at step k thread t meets
+// subgroup (t + k) mod P (P = live subgroups), 16 pairs per visit through ring_visit.  The reaction on the
+// partner subgroup cannot travel by SHFL across warps, so it is accumulated into a per-warp row in shared
+// memory (two 16-byte read-modify-writes per 16 pairs; lane t - 1 touches the same words one step later,
+// hence the warp fence after every step) and the rows are summed in fixed order after the barrier.
+// Decay handling, staging area and centre sums are those of ensemble_pair_kernel.  Needs capT >= 32 (a
+// warp spans at most two nuclei): 125 .. 1024 nucleons.
+struct QuadSmem {
+    float4 *X4, *Y4, *T4;     // [2 * G * capT] subgroups, mirrored at +P so that t + k needs no modulo
+    float4* spc;              // [G * 4 capT] staging (x, y, type, -), touched when a nucleus decays
+    float4* wsum;             // [warps] coordinate sums by nucleus
+    float2* sv;               // [G * 4 capT] staging velocities
+    float2* react;            // [warps][G * 4 capT] reaction rows
+    int* scnt;                // [G]
+};
+
+static size_t quad_smem_bytes(int T, int G, int capT)
+{
+    const size_t nW = T / 32, nSub = (size_t)G * capT, nSlots = 4 * nSub;
+    return sizeof(float4) * (3 * 2 * nSub + nSlots + nW) + sizeof(float2) * (nSlots + nW * nSlots) +
+           sizeof(int) * G + 16;
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 512 / MAXT) ensemble_quad_kernel(const pyqmd_ensemble e,
+                                                                         const LawParams L,
+                                                                         const int n_steps, const int G,
+                                                                         const int capT)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int nW = T >> 5;
+    const int capS = kQ * capT;
+    const int nSub = G * capT;
+    const int nSlots = G * capS;
+    QuadSmem S;
+    S.X4 = reinterpret_cast<float4*>(smem_raw);
+    S.Y4 = S.X4 + 2 * nSub;
+    S.T4 = S.Y4 + 2 * nSub;
+    S.spc = S.T4 + 2 * nSub;
+    S.wsum = S.spc + nSlots;
+    S.sv = reinterpret_cast<float2*>(S.wsum + nW);
+    S.react = S.sv + nSlots;
+    S.scnt = reinterpret_cast<int*>(S.react + nW * nSlots);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int g = tid / capT;
+    const int t = tid - g * capT;
+    const int gb = g * capS;             // slot base (spc, sv, react)
+    const int gb2 = 2 * g * capT;        // subgroup base in the mirrored arrays
+    const int s0 = kQ * t;
+    const int64_t q = (int64_t)blockIdx.x * G + g;
+    const bool has_nuc = (g < G) && (q < e.n_list);
+    const int nuc = has_nuc ? (e.list ? e.list[q] : (int)q) : -1;
+    const bool leader = has_nuc && t == 0;
+
+    int cnt = 0;
+    int64_t off = 0;
+    if (has_nuc) {
+        cnt = e.count[nuc];
+        off = e.offset[nuc];
+    }
+    int P = (cnt + kQ - 1) / kQ;
+    bool active = has_nuc && t < P;
+    float xi[kQ], yi[kQ], ti[kQ];
+    float2 vi[kQ];
+#pragma unroll
+    for (int k = 0; k < kQ; ++k) {
+        xi[k] = kGhost; yi[k] = kGhost; ti[k] = 0.f;
+        vi[k] = make_float2(0.f, 0.f);
+        if (active && s0 + k < cnt) {
+            const float2 p = reinterpret_cast<const float2*>(e.pos)[off + s0 + k];
+            vi[k] = reinterpret_cast<const float2*>(e.vel)[off + s0 + k];
+            xi[k] = p.x; yi[k] = p.y;
+            ti[k] = e.is_proton[off + s0 + k] ? 1.0f : 0.0f;
+        }
+    }
+    // own subgroup -> shared memory (both copies), and the nucleus' coordinate sums (:242-243)
+    auto publish = [&]() {
+        if (active) {
+            const float4 X = make_float4(xi[0], xi[1], xi[2], xi[3]);
+            const float4 Y = make_float4(yi[0], yi[1], yi[2], yi[3]);
+            const float4 Tt = make_float4(ti[0], ti[1], ti[2], ti[3]);
+            S.X4[gb2 + t] = X; S.X4[gb2 + t + P] = X;
+            S.Y4[gb2 + t] = Y; S.Y4[gb2 + t + P] = Y;
+            S.T4[gb2 + t] = Tt; S.T4[gb2 + t + P] = Tt;
+        }
+        float px = 0.f, py = 0.f;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k)
+            if (active && s0 + k < cnt) { px += xi[k]; py += yi[k]; }
+        publish_pair_sums(S.wsum, capT, g, px, py);
+    };
+    if (t == 0 && g < G) S.scnt[g] = cnt;
+    for (int k = tid; k < nW * nSlots; k += T) S.react[k] = make_float2(0.f, 0.f);
+    publish();
+    const int w_lo = (g * capT) >> 5;
+    const int w_hi = min((g * capT + capT - 1) >> 5, nW - 1);
+
+    int32_t zn = 0;
+    double T_half = 0.0, p_dec = -1.0;
+    if (leader && e.decay_enabled) {
+        zn = e.zn[nuc];
+        T_half = e.half_life[nuc];
+        p_dec = e.p_decay[nuc];
+    }
+    const DrawSource draws{e.uniforms, e.seed, e.uniforms_n};
+    const GenConsts gc = make_gen_consts(L);
+    const f32x2 negC = pk1(-L.C);
+    float R = 2.4f * cbrtf((float)cnt);                     // nuclear_forces.py:304
+
+    for (int s = 0; s < n_steps; ++s) {
+        // ---- decay test: Nucleus.should_decay, particles.py:126-147 --------------------------
+        if (e.decay_enabled) {
+            bool fire = false;
+            const uint32_t step_abs = e.step0 + (uint32_t)s;
+            if (leader && p_dec >= 0.0) {                   // stable: no draw (:129-130)
+                const double u0 = draws.one((uint64_t)(e.id_base + nuc), nuc, step_abs, s, 0);
+                fire = u0 < p_dec;                          // :147
+            }
+            if (__syncthreads_or(fire)) {
+#pragma unroll
+                for (int k = 0; k < kQ; ++k)
+                    if (active && s0 + k < cnt) {
+                        S.spc[gb + s0 + k] = make_float4(xi[k], yi[k], ti[k], 0.f);
+                        S.sv[gb + s0 + k] = vi[k];
+                    }
+                __syncthreads();
+                if (fire) {
+                    leader_decay(e, draws, S.spc, S.sv, gb, cnt, nuc, step_abs, s, zn, T_half, p_dec);
+                    S.scnt[g] = cnt;
+                }
+                __syncthreads();
+                if (g < G) cnt = S.scnt[g];
+                P = (cnt + kQ - 1) / kQ;
+                active = has_nuc && t < P;
+#pragma unroll
+                for (int k = 0; k < kQ; ++k) {
+                    xi[k] = kGhost; yi[k] = kGhost; ti[k] = 0.f;
+                    vi[k] = make_float2(0.f, 0.f);
+                    if (active && s0 + k < cnt) {
+                        const float4 a = S.spc[gb + s0 + k];
+                        xi[k] = a.x; yi[k] = a.y; ti[k] = a.z;
+                        vi[k] = S.sv[gb + s0 + k];
+                    }
+                }
+                __syncthreads();                            // staging consumed before the subgroups move
+                R = 2.4f * cbrtf((float)cnt);
+                publish();
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();             // subgroups and sums of this sub-step are in shared memory
+        }
+
+        float fx[kQ], fy[kQ];
+        float cx = 0.f, cy = 0.f;
+        f32x2 ax[kQ], ay[kQ], xi2[kQ], yi2[kQ];
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) {
+            ax[k] = 0ull; ay[k] = 0ull;
+            xi2[k] = pk1(xi[k]);
+            yi2[k] = pk1(yi[k]);
+        }
+        if (active) {
+            // ---- centre of mass, nuclear_forces.py:242-243 ----------------------------------------
+            if (e.centre) {                                 // caller-supplied `center`, :64
+                cx = e.centre[2 * (int64_t)nuc];
+                cy = e.centre[2 * (int64_t)nuc + 1];
+            } else {
+                float sx = 0.f, sy = 0.f;
+                for (int w = w_lo; w <= w_hi; ++w) {
+                    const float4 ws = S.wsum[w];
+                    const int gf = (w << 5) / capT;
+                    if (gf == g) { sx += ws.x; sy += ws.y; }
+                    else if (gf + 1 == g) { sx += ws.z; sy += ws.w; }
+                }
+                const float inv_n = 1.0f / (float)cnt;
+                cx = sx * inv_n;
+                cy = sy * inv_n;
+            }
+            // pairs inside the subgroup: ordered, no reaction (the self pairs are skipped by d2 < 0.01)
+            Reacts none = {0ull, 0ull, 0ull, 0ull};
+            ring_visit<false>(make_ulonglong2(pk(xi[0], xi[1]), pk(xi[2], xi[3])),
+                              make_ulonglong2(pk(yi[0], yi[1]), pk(yi[2], yi[3])),
+                              make_float4(ti[0], ti[1], ti[2], ti[3]), xi2, yi2, ti, ax, ay, none, gc, L,
+                              negC);
+        }
+        // ---- all-pairs force, nuclear_forces.py:248-298: ring over the nucleus' P subgroups -----------
+        {
+            const ulonglong2* Xg = reinterpret_cast<const ulonglong2*>(S.X4 + gb2);
+            const ulonglong2* Yg = reinterpret_cast<const ulonglong2*>(S.Y4 + gb2);
+            const float4* Tg = S.T4 + gb2;
+            float4* row = reinterpret_cast<float4*>(S.react + (size_t)warp * nSlots + gb);
+            auto visit = [&](int u) {                       // partner subgroup u in [0, 2P): mirrored
+                const unsigned ur = min((unsigned)u, (unsigned)(u - P));   // u mod P
+                Reacts r = {0ull, 0ull, 0ull, 0ull};
+                ring_visit<true>(Xg[u], Yg[u], Tg[u], xi2, yi2, ti, ax, ay, r, gc, L, negC);
+                float a0, a1, b0, b1;
+                // (loading the row words before the 16 pairs are evaluated was measured: 1.5 % slower)
+                float4 v = row[2 * ur], w = row[2 * ur + 1];
+                upk(r.x01, a0, a1);                          // slots 4 ur, 4 ur + 1: (x, y, x, y)
+                upk(r.y01, b0, b1);
+                v.x -= a0; v.y -= b0; v.z -= a1; v.w -= b1;
+                row[2 * ur] = v;
+                upk(r.x23, a0, a1);                          // slots 4 ur + 2, 4 ur + 3
+                upk(r.y23, b0, b1);
+                w.x -= a0; w.y -= b0; w.z -= a1; w.w -= b1;
+                row[2 * ur + 1] = w;
+            };
+            // trip counts differ between the (at most two) nuclei of a warp: every lane runs the warp's
+            // maximum and masks its own visits, so that the fence after each step is warp-wide
+            const int hs = active ? ((P - 1) >> 1) : 0;
+            const int hs_w = __reduce_max_sync(0xffffffffu, hs);
+            for (int k = 1; k <= hs_w; ++k) {
+                if (k <= hs) visit(t + k);
+                __syncwarp();            // lane t - 1 updates at step k + 1 the words lane t wrote at step k
+            }
+            if (active && !(P & 1) && t < (P >> 1)) visit(t + (P >> 1));   // antipodal subgroup, even P
+        }
+        __syncthreads();                 // Jacobi: all reads (and all reactions) before any write
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < kQ; ++k) {
+                float a, b;
+                upk(ax[k], a, b); fx[k] = a + b;
+                upk(ay[k], a, b); fy[k] = a + b;
+            }
+            for (int w = w_lo; w <= w_hi; ++w) {            // fixed order: reproducible
+                float4* rw = reinterpret_cast<float4*>(S.react + (size_t)w * nSlots + gb) + 2 * t;
+                const float4 ra = rw[0], rb = rw[1];
+                rw[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rw[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fx[0] += ra.x; fy[0] += ra.y; fx[1] += ra.z; fy[1] += ra.w;
+                fx[2] += rb.x; fy[2] += rb.y; fx[3] += rb.z; fy[3] += rb.w;
+            }
+#pragma unroll
+            for (int k = 0; k < kQ; ++k)
+                if (s0 + k < cnt) {
+                    contain_and_integrate(xi[k], yi[k], vi[k].x, vi[k].y, fx[k], fy[k], cx, cy, R,
+                                          e.dt_phys);              // :301-323
+                    if (e.force && s == n_steps - 1)
+                        reinterpret_cast<float2*>(e.force)[off + s0 + k] = make_float2(fx[k], fy[k]);
+                }
+        }
+        publish();
+    }
+
+#pragma unroll
+    for (int k = 0; k < kQ; ++k)
+        if (active && s0 + k < cnt) {
+            reinterpret_cast<float2*>(e.pos)[off + s0 + k] = make_float2(xi[k], yi[k]);
+            reinterpret_cast<float2*>(e.vel)[off + s0 + k] = vi[k];
+            e.is_proton[off + s0 + k] = (ti[k] != 0.f) ? 1 : 0;
+        }
+    if (leader) {
+        e.count[nuc] = cnt;
+        if (e.decay_enabled) {
+            e.zn[nuc] = zn;
+            e.half_life[nuc] = T_half;
+            e.p_decay[nuc] = p_dec;
+        }
+    }
+}
+
+// block shape of the quad kernel: G nuclei x capT threads in T in {128, 160, 224, 256} threads, the choice
+// that keeps most lanes busy on most resident warps (128 registers per thread: 512 threads per SM)
+static int pick_quad_threads(int capT, int* G_out)
+{
+    static const int shapes[4] = {128, 160, 224, 256};
+    int best_T = 0, best_G = 0;
+    double best = -1.0;
+    const char* pin = getenv("PYQMD_QUAD_THREADS");         // tuning runs
+    for (int T : shapes) {
+        if (pin && atoi(pin) != T) continue;
+        const int G = T / capT;
+        if (G < 1) continue;
+        const size_t sm = quad_smem_bytes(T, G, capT);
+        int blocks = 512 / T;
+        const int by_smem = (int)((size_t)220 * 1024 / (sm + 1024));
+        if (by_smem < blocks) blocks = by_smem;
+        if (blocks < 1) continue;
+        const double score = (double)G * capT / T * (blocks * (T / 32));
+        if (score > best + 1e-9) { best = score; best_T = T; best_G = G; }
+    }
+    *G_out = best_G;
+    return best_T;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
 // ensemble_cluster_kernel: ONE nucleus on a thread-block CLUSTER of 8 CTAs (8 SMs), for launches of a
 // handful of nuclei (BASELINE config 1: a single U-238; the interactive app).  Such a launch cannot
 // fill the GPU, its sub-steps are a latency chain -- 21 us each in one CTA -- so the chain is cut
@@ -1159,6 +1457,13 @@ static int configure_ensemble_kernels(void)
         PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
     }
+    const void* quads[4] = {(const void*)ensemble_quad_kernel<128>, (const void*)ensemble_quad_kernel<160>,
+                            (const void*)ensemble_quad_kernel<224>, (const void*)ensemble_quad_kernel<256>};
+    for (const void* k : quads) {
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PYQMD_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
+    }
     if (dev >= 0 && dev < 64) done[dev] = 1;
     return PYQMD_OK;
 }
@@ -1199,6 +1504,36 @@ extern "C" int pyqmd_ensemble_step(const pyqmd_ensemble* e, int32_t n_steps, voi
             PYQMD_REQUIRE(n_list <= 2147483647LL / kClusterSize, "too many nuclei for one launch");
             ensemble_cluster_kernel<<<(unsigned)(n_list * kClusterSize), kClusterThreads, sm, st>>>(
                 d, L, n_steps, capP, ipc);
+            PYQMD_CUDA_CHECK(cudaGetLastError());
+            return PYQMD_OK;
+        }
+    }
+    // block-wide ring with four nucleons per thread (ensemble_quad_kernel): ring_visit's instruction count
+    // at the block ring's lane utilisation.  PYQMD_ENSEMBLE_KERNEL=quad selects it.
+    {
+        const int capQ = (e->cap + kQ - 1) / kQ;
+        int Gq = 0;
+        const int Tq = capQ >= 32 ? pick_quad_threads(capQ, &Gq) : 0;
+        const char* force = getenv("PYQMD_ENSEMBLE_KERNEL");
+        bool use_quad = false;
+        if (Tq > 0) {
+            // Not dispatched automatically.  Measured on B200 (r02m, pairs/s, quad / block ring / warp rings):
+            // one sub-step per launch Pb-208 1.166e12 / 1.144e12 / 1.045e12, Au-197 1.089e12 / 1.073e12 / 0.98e12,
+            // U-238 1.170e12 / - / 1.200e12; FOUR fused sub-steps per launch (the app's frame) Pb-208 1.100e12
+            // against the block ring's 1.171e12: its best shape, 3 nuclei on 160 threads, puts 5 warps per block
+            // and 15 per SM on 4 schedulers, and the two block barriers of every sub-step wait for the scheduler
+            // that holds two of them (ncu: barrier stalls 0.27 -> 1.06 per issued instruction from 1 to 4
+            // sub-steps).  Kept as a pinned alternative; every parity case runs through it.
+            if (force) use_quad = !strcmp(force, "quad");
+        }
+        if (use_quad) {
+            const size_t sm = quad_smem_bytes(Tq, Gq, capQ);
+            const int64_t gridq = (n_list + Gq - 1) / Gq;
+            PYQMD_REQUIRE(gridq <= 2147483647LL, "too many nuclei for one launch");
+            if (Tq == 128) ensemble_quad_kernel<128><<<(unsigned)gridq, Tq, sm, st>>>(d, L, n_steps, Gq, capQ);
+            else if (Tq == 160) ensemble_quad_kernel<160><<<(unsigned)gridq, Tq, sm, st>>>(d, L, n_steps, Gq, capQ);
+            else if (Tq == 224) ensemble_quad_kernel<224><<<(unsigned)gridq, Tq, sm, st>>>(d, L, n_steps, Gq, capQ);
+            else ensemble_quad_kernel<256><<<(unsigned)gridq, Tq, sm, st>>>(d, L, n_steps, Gq, capQ);
             PYQMD_CUDA_CHECK(cudaGetLastError());
             return PYQMD_OK;
         }

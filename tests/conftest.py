@@ -63,11 +63,12 @@ def u238_traj():
     return dict(np.load(os.path.join(GOLD, "u238_traj.npz")))
 
 
-@pytest.fixture(params=["ring", "block", "cluster"])
+@pytest.fixture(params=["ring", "block", "quad", "cluster"])
 def ensemble_kernel(request, monkeypatch):
-    """Pins pyqmd_ensemble_step's choice between the warp-local ring kernel, the block-wide ring and the
-    8-CTA cluster kernel (csrc/ensemble.cu) so that ALL of them see the parity case, whatever the automatic
-    dispatch would pick for its size ("cluster" applies to nuclei of 64..512 nucleons, others take the
-    automatic choice)."""
+    """Pins pyqmd_ensemble_step's choice between the warp-local ring kernel, the block-wide ring (two
+    nucleons per thread), the block-wide ring with four nucleons per thread ("quad") and the 8-CTA cluster
+    kernel (csrc/ensemble.cu) so that ALL of them see the parity case, whatever the automatic dispatch would
+    pick for its size ("cluster" applies to nuclei of 64..512 nucleons, "quad" to 125..1024; others take
+    the automatic choice)."""
     monkeypatch.setenv("PYQMD_ENSEMBLE_KERNEL", request.param)
     return request.param
